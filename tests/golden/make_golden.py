@@ -1,0 +1,179 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ from the REAL reference.
+
+Run in the build container only (needs /root/reference; the GPU box does not
+have it):
+
+    python tests/golden/make_golden.py
+
+It imports the unmodified reference package from /root/reference, runs its
+numba hot path (schpf/hpf_numba.py, schpf/scHPF_.py:_fit, schpf/loss.py) on
+seeded inputs and stores inputs + outputs as small .npz files.  The oracle
+(oracle/) and the CUDA path (schpf_b200/) are both checked against these.
+
+Fixtures
+  kernels_k4.npz    the reference's own test fixture recipe (tests/conftest.py:
+                    seed 42, 300 x 1000, 3 % fill, K = 4, fp64) and the output
+                    of each of the six kernels on it (tests/test_inference.py).
+  cavi_cfg1.npz     BASELINE cfg-1 (1k x 2k, 100 draws/cell, K = 5): state
+                    after 1, 10 and 50 iterations of scHPF._fit from a seeded
+                    init (reinit=False, min_iter=max_iter) + loss lists.
+  project_cfg1.npz  scHPF.project of 200 held-out cells onto the 50-iteration
+                    model (genes frozen): projected xi/theta + loss.
+  reinit_small.npz  fit with reinit=True (the t==0 Dirichlet branch) under a
+                    fixed numpy seed: final state + loss.
+  simul_small.npz   beta_theta_simultaneous=True variant of the loop.
+"""
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("SCHPF_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+import schpf                                    # noqa: E402  (the reference)
+from schpf import scHPF, hpf_numba              # noqa: E402
+from scipy.sparse import coo_matrix             # noqa: E402
+
+from schpf_b200.synth import synth_coo          # noqa: E402
+
+assert os.path.realpath(schpf.__file__).startswith(os.path.realpath(REF)), schpf.__file__
+
+
+def state_dict(model, prefix=""):
+    return {
+        prefix + "theta_shp": model.theta.vi_shape.copy(), prefix + "theta_rte": model.theta.vi_rate.copy(),
+        prefix + "beta_shp": model.beta.vi_shape.copy(), prefix + "beta_rte": model.beta.vi_rate.copy(),
+        prefix + "xi_shp": model.xi.vi_shape.copy(), prefix + "xi_rte": model.xi.vi_rate.copy(),
+        prefix + "eta_shp": model.eta.vi_shape.copy(), prefix + "eta_rte": model.eta.vi_rate.copy(),
+    }
+
+
+def kernels_k4():
+    # tests/conftest.py:8-38 recipe
+    np.random.seed(42)
+    N_CELLS, N_GENES, NZ_FRAC, N_FACTORS = (300, 1000, 0.03, 4)
+    NNZ = int(N_CELLS * N_GENES * NZ_FRAC)
+    X_data = np.random.negative_binomial(2, 0.5, NNZ)
+    X_data[X_data == 0] = 1
+    cell_ix = np.random.randint(0, N_CELLS, NNZ, dtype=np.int32)
+    gene_ix = np.random.randint(0, N_GENES, NNZ, dtype=np.int32)
+    X = coo_matrix((X_data, (cell_ix, gene_ix)), (N_CELLS, N_GENES), dtype=np.int32)
+    X.sum_duplicates()
+    model = scHPF(N_FACTORS, dtype=np.float64)
+    model._initialize(X)
+    random_phi = np.random.dirichlet(np.ones(N_FACTORS), X.data.shape[0])
+    Xphi_rand = X.data[:, None] * random_phi
+
+    out = dict(row=X.row.astype(np.int32), col=X.col.astype(np.int32),
+               data=X.data.astype(np.int32), shape=np.array(X.shape),
+               a=model.a, ap=model.ap, bp=model.bp, c=model.c, cp=model.cp, dp=model.dp,
+               Xphi_rand=Xphi_rand)
+    out.update(state_dict(model))
+    th, be, xi, eta = model.theta, model.beta, model.xi, model.eta
+    out["Xphi"] = hpf_numba.compute_Xphi_data(X.data, X.row, X.col, th.vi_shape, th.vi_rate,
+                                              be.vi_shape, be.vi_rate)
+    out["theta_shape_upd"] = hpf_numba.compute_loading_shape_update(Xphi_rand, X.row, N_CELLS, model.a)
+    out["beta_shape_upd"] = hpf_numba.compute_loading_shape_update(Xphi_rand, X.col, N_GENES, model.c)
+    out["theta_rate_upd"] = hpf_numba.compute_loading_rate_update(xi.vi_shape, xi.vi_rate,
+                                                                  be.vi_shape, be.vi_rate)
+    out["beta_rate_upd"] = hpf_numba.compute_loading_rate_update(eta.vi_shape, eta.vi_rate,
+                                                                 th.vi_shape, th.vi_rate)
+    out["eta_rate_upd"] = hpf_numba.compute_capacity_rate_update(be.vi_shape, be.vi_rate, model.dp)
+    out["xi_rate_upd"] = hpf_numba.compute_capacity_rate_update(th.vi_shape, th.vi_rate, model.bp)
+    out["llh"] = hpf_numba.compute_pois_llh(X.data, X.row, X.col, th.vi_shape, th.vi_rate,
+                                            be.vi_shape, be.vi_rate)
+    out["mean_neg_llh"] = model.mean_negative_pois_llh(X)
+    out["cell_score"] = model.cell_score()
+    out["gene_score"] = model.gene_score()
+    xs = np.array([1e-4, 1e-3, 1e-2, 0.1, 1, 10, 100, 1000], dtype=np.float64)   # tests/test_inference.py:24
+    out["psi_x"] = xs
+    out["psi_y"] = np.array([hpf_numba.psi(x) for x in xs])
+    out["gammaln_y"] = np.array([hpf_numba.cgammaln(x) for x in xs])
+    np.savez_compressed(os.path.join(HERE, "kernels_k4.npz"), **out)
+    print("kernels_k4: nnz", X.nnz)
+
+
+def cavi_cfg1():
+    X = synth_coo(1000, 2000, 100, 5, seed=0)
+    out = dict(row=X.row.astype(np.int32), col=X.col.astype(np.int32),
+               data=X.data.astype(np.int32), shape=np.array(X.shape))
+    np.random.seed(1)
+    base = scHPF(5, verbose=False)
+    base._initialize(X)
+    out.update(dict(a=base.a, ap=base.ap, bp=base.bp, c=base.c, cp=base.cp, dp=base.dp))
+    out.update(state_dict(base, "init_"))
+    final = None
+    for n, cf in ((1, 1), (10, 3), (50, 10)):
+        from copy import deepcopy
+        m = deepcopy(base)
+        m.fit(X, reinit=False, min_iter=n, max_iter=n, check_freq=cf, verbose=False)
+        out.update(state_dict(m, "it%d_" % n))
+        out["it%d_loss" % n] = np.array(m.loss)
+        out["it%d_check_freq" % n] = cf
+        final = m
+    np.savez_compressed(os.path.join(HERE, "cavi_cfg1.npz"), **out)
+    print("cavi_cfg1: nnz", X.nnz, "loss50", final.loss)
+
+    # ---- projection of held-out cells onto the 50-iteration model ----------
+    Xn = synth_coo(200, 2000, 100, 5, seed=7)
+    np.random.seed(3)
+    proj = final.project(Xn, min_iter=10, max_iter=10, check_freq=2, verbose=False)
+    pout = dict(row=Xn.row.astype(np.int32), col=Xn.col.astype(np.int32),
+                data=Xn.data.astype(np.int32), shape=np.array(Xn.shape),
+                bp=proj.bp, loss=np.array(proj.loss), seed=3,
+                theta_shp=proj.theta.vi_shape, theta_rte=proj.theta.vi_rate,
+                xi_shp=proj.xi.vi_shape, xi_rte=proj.xi.vi_rate,
+                cell_score=proj.cell_score())
+    # the exact init the projection started from (np.random.seed(3) then _setup order)
+    np.random.seed(3)
+    from schpf import HPF_Gamma
+    xi0 = HPF_Gamma.random_gamma_factory((200,), final.ap, final.bp)
+    th0 = HPF_Gamma.random_gamma_factory((200, 5), final.a, final.bp)
+    pout.update(init_xi_shp=xi0.vi_shape, init_xi_rte=xi0.vi_rate,
+                init_theta_shp=th0.vi_shape, init_theta_rte=th0.vi_rate)
+    np.savez_compressed(os.path.join(HERE, "project_cfg1.npz"), **pout)
+    print("project_cfg1: loss", proj.loss)
+
+
+def reinit_small():
+    X = synth_coo(200, 300, 40, 3, seed=5)
+    np.random.seed(11)
+    m = scHPF(3, verbose=False)
+    m.fit(X, min_iter=6, max_iter=6, check_freq=2, verbose=False)    # reinit=True default
+    out = dict(row=X.row.astype(np.int32), col=X.col.astype(np.int32),
+               data=X.data.astype(np.int32), shape=np.array(X.shape), seed=11,
+               bp=m.bp, dp=m.dp, loss=np.array(m.loss))
+    out.update(state_dict(m))
+    np.savez_compressed(os.path.join(HERE, "reinit_small.npz"), **out)
+    print("reinit_small: loss", m.loss)
+
+
+def simul_small():
+    X = synth_coo(200, 300, 40, 3, seed=5)
+    np.random.seed(12)
+    base = scHPF(3, verbose=False)
+    base._initialize(X)
+    out = dict(row=X.row.astype(np.int32), col=X.col.astype(np.int32),
+               data=X.data.astype(np.int32), shape=np.array(X.shape),
+               a=base.a, ap=base.ap, bp=base.bp, c=base.c, cp=base.cp, dp=base.dp)
+    out.update(state_dict(base, "init_"))
+    base.fit(X, reinit=False, min_iter=7, max_iter=7, check_freq=2, verbose=False,
+             beta_theta_simultaneous=True)
+    out.update(state_dict(base, "fin_"))
+    out["loss"] = np.array(base.loss)
+    np.savez_compressed(os.path.join(HERE, "simul_small.npz"), **out)
+    print("simul_small: loss", base.loss)
+
+
+if __name__ == "__main__":
+    kernels_k4()
+    cavi_cfg1()
+    reinit_small()
+    simul_small()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
