@@ -1,0 +1,236 @@
+// Shared declarations for the schpf_b200 CUDA library (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/schpf_b200.h"
+
+namespace schpf {
+
+// ---------------------------------------------------------------- errors ----
+void set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                               \
+    do {                                                                             \
+        cudaError_t e__ = (expr);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            ::schpf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,         \
+                               cudaGetErrorString(e__));                             \
+            return SCHPF_ERR_CUDA;                                                   \
+        }                                                                            \
+    } while (0)
+
+#define RC_TRY(expr)                                                                 \
+    do {                                                                             \
+        int rc__ = (expr);                                                           \
+        if (rc__ != SCHPF_OK) return rc__;                                           \
+    } while (0)
+
+// ------------------------------------------------------- table geometry ----
+// The sweep kernels give every nonzero to a PAIR of lanes; lane h of the pair
+// owns the 16-byte units {2j+h} of a K-row, so rows are padded to KP = a
+// multiple of 4 doubles.  Rows are stored with a stride ST chosen so that
+// ST*8/32 is odd: then the 32-byte piece a lane pair reads in one LDS.128 lands
+// in shared-memory bank group (row + j) mod 4, and four pairs reading rows of
+// four different residues mod 4 never collide.
+__host__ __device__ constexpr int kp_of(int K) { return (K + 3) & ~3; }
+__host__ __device__ constexpr int stride_of_kp(int KP) { return ((KP / 4) & 1) ? KP : KP + 4; }
+
+constexpr int GROUPS_PER_WARP = 16;          // lane pairs
+constexpr double TINY_NORMALIZER = 1e-280;   // below this the factored softmax is redone in log space
+
+// ------------------------------------------------------- device helpers ----
+#define SCHPF_EULER 0.57721566490153286061
+
+// digamma for x > 0: upward recurrence to x >= 10, then the Bernoulli
+// asymptotic series (Abramowitz & Stegun 6.3.18); exact harmonic numbers for
+// integers <= 10.  Same arithmetic as oracle/hpf_oracle.c:oracle_psi; checked
+// against scipy.special.digamma in tests/test_gpu_kernels.py.
+__device__ __forceinline__ double digamma_pos(double x)
+{
+    if (!(x > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+    if (x <= 10.0 && x == floor(x)) {
+        double y = 0.0;
+        for (int i = (int)x - 1; i >= 1; --i) y += 1.0 / (double)i;
+        return y - SCHPF_EULER;
+    }
+    double s = x, w = 0.0;
+    while (s < 10.0) {
+        w += 1.0 / s;
+        s += 1.0;
+    }
+    double y = 0.0;
+    if (s < 1.0e17) {
+        const double z = 1.0 / (s * s);
+        double p = 8.33333333333333333333e-2;
+        p = p * z - 2.10927960927960927961e-2;
+        p = p * z + 7.57575757575757575758e-3;
+        p = p * z - 4.16666666666666666667e-3;
+        p = p * z + 3.96825396825396825397e-3;
+        p = p * z - 8.33333333333333333333e-3;
+        p = p * z + 8.33333333333333333333e-2;
+        y = z * p;
+    }
+    return log(s) - 0.5 / s - y - w;
+}
+
+// y / s for a normal positive s: hardware seed (MUFU.RCP64H, ~20 bits), two
+// Newton steps, then one residual correction of the quotient (error < 1 ulp).
+__device__ __forceinline__ double div_pos(double y, double s)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+    double e = fma(-s, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-s, r, 1.0);
+    r = fma(r, e, r);
+    double q = y * r;
+    const double rem = fma(-s, q, y);
+    return fma(rem, r, q);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) -------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// streaming 128-bit load that does not allocate in L1 (entry stream is read once)
+__device__ __forceinline__ int4 ld_stream_int4(const int4 *p)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------ layouts ------
+// One "side" of the two-pass sweep: the OWNER axis keeps its K-row and its
+// accumulators in registers, the OTHER axis is streamed through shared memory
+// in panels of `panel_rows` rows.  See DESIGN.md §3.
+struct SideLayout {
+    int64_t n_own = 0, n_oth = 0;
+    int panel_rows = 0;        // Po
+    int npanel = 0;
+    int warps = 0;             // W warps per CTA; W*16 owners per CTA block
+    int nblocks = 0;           // owner blocks
+    int panels_per_range = 0;  // PR
+    int nranges = 0;
+    int64_t total_pairs = 0;   // warp-steps / 2
+    int64_t padded_entries = 0;
+    int32_t *own_id = nullptr;   // [nblocks * W * 16] slot -> owner id, -1 = empty slot
+    int64_t *seg_ptr = nullptr;  // [(nblocks * W) * (npanel + 1)] in step pairs
+    int4 *entries = nullptr;     // [total_pairs * 16] : {oth_local|pad, y, oth_local|pad, y}
+    size_t bytes = 0;
+    void release();
+};
+
+int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int32_t *d_own,
+                      const int32_t *d_oth, const int32_t *d_val, int64_t n_own, int64_t n_oth,
+                      int panel_rows, int warps, int target_ctas);
+
+// ------------------------------------------------------------- sweeps ------
+enum SweepMode { SWEEP_SHAPE = 0, SWEEP_LLH = 1 };
+
+struct SweepArgs {
+    const int32_t *own_id;
+    const int64_t *seg_ptr;
+    const int4 *entries;
+    const double *own_tab;   // [n_own x ST]   owner-side table (factored exp / e_x)
+    const double *oth_tab;   // [npanel*Po x ST]
+    double *acc;             // SHAPE: [n_own x K] sum_i w_i * oth_tab[oth_i, k]   (atomicAdd)
+    double *partial;         // LLH:   [gridDim.x] sum (y log r - r)
+    const double *own_elog;  // [n_own x K]  log-space fallback
+    const double *oth_elog;  // [n_oth x K]
+    double *direct;          // [n_own x K]  fallback contributions, already y*phi
+    unsigned long long *slow_hits;
+    int K;
+    int npanel, panel_rows, warps, panels_per_range, nranges;
+};
+
+int launch_sweep(int mode, int K, const SideLayout &L, const SweepArgs &args, cudaStream_t stream);
+size_t sweep_smem_bytes(int K, int panel_rows);
+int max_panel_rows(int K, int ctas_per_sm);
+
+// ------------------------------------------------ dense / per-nnz kernels ---
+int launch_prep_side(cudaStream_t s, int64_t n, int K, const double *shp, const double *rte,
+                     double *elog, double *E, double *colsum /* K, accumulated; may be null */);
+int launch_ex_table(cudaStream_t s, int64_t n, int K, const double *shp, const double *rte, double *X);
+int launch_fold(cudaStream_t s, int64_t n, int K, const double *E, const double *acc,
+                const double *direct, double *out);
+int launch_finalize(cudaStream_t s, int64_t n, int K, double prior_shape, double prior_rate,
+                    const double *folded /* n x K, or null */, const double *E, const double *acc,
+                    const double *direct, const double *other_colsum, const double *cap_shp,
+                    double *cap_rte, double *shp, double *rte, double *elog, double *Etab,
+                    double *colsum_out);
+int launch_literal(cudaStream_t s, int64_t nnz, int K, const int32_t *row, const int32_t *col,
+                   const int32_t *data, const double *elog_t, const double *elog_b,
+                   double *xphi_out, double *direct_t, double *direct_b);
+int launch_random_phi(cudaStream_t s, int64_t nnz, int K, const int32_t *row, const int32_t *col,
+                      const int32_t *data, uint64_t seed, int64_t row_offset, double *direct_t,
+                      double *direct_b);
+int launch_scatter_xphi(cudaStream_t s, int64_t nnz, int K, const double *xphi, const int32_t *keep,
+                        double *out);
+int launch_llh_pointwise(cudaStream_t s, int64_t nnz, int K, const int32_t *row, const int32_t *col,
+                         const int32_t *data, const double *ts, const double *tr, const double *bs,
+                         const double *br, double *out);
+int launch_lgamma_sum(cudaStream_t s, int64_t nnz, const int32_t *data, double *partials, int nblk,
+                      double *out);
+int launch_sum_partials(cudaStream_t s, const double *partials, int n, double *out);
+int launch_validate_coo(cudaStream_t s, int64_t nnz, const int32_t *row, const int32_t *col,
+                        const int32_t *data, int64_t C, int64_t G, int *flag);
+int launch_fill(cudaStream_t s, double *p, int64_t n, double v);
+int launch_psi(cudaStream_t s, int64_t n, const double *x, double *out, int which);
+int launch_rate_update(cudaStream_t s, int64_t n, int K, const double *pshp, const double *prte,
+                       const double *colsum, double *out);
+int launch_colsum_ex(cudaStream_t s, int64_t m, int K, const double *shp, const double *rte,
+                     double *colsum);
+int launch_capacity_rate(cudaStream_t s, int64_t n, int K, const double *shp, const double *rte,
+                         double prior, double *out);
+
+}  // namespace schpf

@@ -1,0 +1,782 @@
+// Engine-level C ABI: the loop body of the reference's scHPF._fit
+// (schpf/scHPF_.py:642-715) with the count matrix and the eight variational
+// arrays resident in HBM.  See include/schpf_b200.h for the contract.
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace schpf {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int sweep_ctas_per_sm(int K);
+int sweep_default_warps(int K);
+
+}  // namespace schpf
+
+using namespace schpf;
+
+struct schpf_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t C = 0, G = 0, nnz = 0;
+    int K = 0, ST = 0;
+    int64_t C_pad = 0, G_pad = 0;
+
+    // options
+    int opt_panel_rows = 0;     // 0 = largest that fits
+    int opt_warps = 0;          // 0 = the most the register budget allows for this K
+    int opt_target_ctas = 2368; // 148 SMs x 2 CTAs x 8 waves
+    int opt_variant = 0;
+    int opt_timing = 0;
+    int64_t row_offset = 0;     // global index of local cell 0 (random-phi stream)
+
+    bool have_coo = false, have_hyper = false, have_state = false;
+    bool tables_t_valid = false, tables_b_valid = false;
+    double a = 0, ap = 0, bp = 0, c = 0, cp = 0, dp = 0;
+
+    // state (unpadded, row-major)
+    double *theta_shp = nullptr, *theta_rte = nullptr, *beta_shp = nullptr, *beta_rte = nullptr;
+    double *xi_shp = nullptr, *xi_rte = nullptr, *eta_shp = nullptr, *eta_rte = nullptr;
+    // tables
+    double *Et = nullptr, *Eb = nullptr;            // [C_pad x ST], [G_pad x ST]
+    double *elog_t = nullptr, *elog_b = nullptr;    // [C x K], [G x K]
+    // accumulators: one allocation [acc_t | direct_t | acc_b | direct_b]
+    double *accum = nullptr;
+    double *acc_t = nullptr, *direct_t = nullptr, *acc_b = nullptr, *direct_b = nullptr;
+    double *exch = nullptr;                          // [G*K | K]
+    double *colsum_b = nullptr, *colsum_t_next = nullptr;   // [K]
+    double *partials = nullptr;                      // llh / lgamma block partials
+    int partials_cap = 0;
+    double *scalars = nullptr;                       // [0] llh sum, [1] lgamma sum
+    unsigned long long *slow_hits = nullptr;
+    int *flag = nullptr;
+    double lgamma_sum = 0.0;
+
+    int32_t *row = nullptr, *col = nullptr, *data = nullptr;
+    SideLayout cells, genes;
+
+    // counters
+    double n_iterations = 0, n_sweeps = 0, n_launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    double sweep_ms_accum = 0.0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T **p, int64_t n)
+{
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(p), sizeof(T) * (size_t)(n > 0 ? n : 1)));
+    return SCHPF_OK;
+}
+
+template <typename T>
+void dev_free(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int check_handle(schpf_engine *h)
+{
+    if (!h) {
+        set_error("null engine handle");
+        return SCHPF_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    return SCHPF_OK;
+}
+
+void free_coo(schpf_engine *h)
+{
+    dev_free(h->row);
+    dev_free(h->col);
+    dev_free(h->data);
+    h->cells.release();
+    h->genes.release();
+    h->have_coo = false;
+}
+
+int timed_sweep(schpf_engine *h, int mode, const SideLayout &L, const SweepArgs &args)
+{
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->opt_timing) {
+        if (h->ev_used == h->ev_pool.size()) {
+            cudaEvent_t a, b;
+            CUDA_TRY(cudaEventCreate(&a));
+            CUDA_TRY(cudaEventCreate(&b));
+            h->ev_pool.emplace_back(a, b);
+        }
+        e0 = h->ev_pool[h->ev_used].first;
+        e1 = h->ev_pool[h->ev_used].second;
+        ++h->ev_used;
+        CUDA_TRY(cudaEventRecord(e0, h->stream));
+    }
+    RC_TRY(launch_sweep(mode, h->K, L, args, h->stream));
+    if (h->opt_timing) CUDA_TRY(cudaEventRecord(e1, h->stream));
+    h->n_sweeps += 1;
+    h->n_launches += 1;
+    return SCHPF_OK;
+}
+
+int collect_timing(schpf_engine *h)
+{
+    if (h->ev_used == 0) return SCHPF_OK;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < h->ev_used; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_pool[i].first, h->ev_pool[i].second));
+        h->sweep_ms_accum += ms;
+    }
+    h->ev_used = 0;
+    return SCHPF_OK;
+}
+
+SweepArgs side_args(schpf_engine *h, const SideLayout &L)
+{
+    SweepArgs A;
+    memset(&A, 0, sizeof(A));
+    A.own_id = L.own_id;
+    A.seg_ptr = L.seg_ptr;
+    A.entries = L.entries;
+    A.slow_hits = h->slow_hits;
+    A.K = h->K;
+    A.npanel = L.npanel;
+    A.panel_rows = L.panel_rows;
+    A.warps = L.warps;
+    A.panels_per_range = L.panels_per_range;
+    A.nranges = L.nranges;
+    return A;
+}
+
+// Elog / factored tables and column sums from the current state
+// (hpf_numba.py:83-94; first half of compute_loading_rate_update :167-170)
+int ensure_tables(schpf_engine *h)
+{
+    const int K = h->K;
+    if (!h->tables_t_valid) {
+        CUDA_TRY(cudaMemsetAsync(h->colsum_t_next, 0, sizeof(double) * K, h->stream));
+        RC_TRY(launch_prep_side(h->stream, h->C, K, h->theta_shp, h->theta_rte, h->elog_t, h->Et,
+                                h->colsum_t_next));
+        h->n_launches += 1;
+        h->tables_t_valid = true;
+    }
+    if (!h->tables_b_valid) {
+        CUDA_TRY(cudaMemsetAsync(h->colsum_b, 0, sizeof(double) * K, h->stream));
+        RC_TRY(launch_prep_side(h->stream, h->G, K, h->beta_shp, h->beta_rte, h->elog_b, h->Eb, h->colsum_b));
+        h->n_launches += 1;
+        h->tables_b_valid = true;
+    }
+    return SCHPF_OK;
+}
+
+int require_ready(schpf_engine *h)
+{
+    if (!h->have_coo || !h->have_hyper || !h->have_state) {
+        set_error("engine not ready: set_coo=%d set_hyper=%d set_state=%d", (int)h->have_coo,
+                  (int)h->have_hyper, (int)h->have_state);
+        return SCHPF_ERR_STATE;
+    }
+    return SCHPF_OK;
+}
+
+int zero_accumulators(schpf_engine *h, bool genes_too)
+{
+    const size_t nt = (size_t)h->C * h->K * 2, nb = (size_t)h->G * h->K * 2;
+    CUDA_TRY(cudaMemsetAsync(h->accum, 0, sizeof(double) * (nt + (genes_too ? nb : 0)), h->stream));
+    return SCHPF_OK;
+}
+
+// mode 0: E-step from the resident state; 1: random phi; 2: Xphi supplied (already scattered by caller)
+int step_begin_impl(schpf_engine *h, int flags, int mode, uint64_t seed)
+{
+    const bool freeze = flags & SCHPF_FREEZE_GENES;
+    const int K = h->K;
+    RC_TRY(ensure_tables(h));
+    if (mode != 2) RC_TRY(zero_accumulators(h, !freeze));
+    if (mode == 1) {
+        RC_TRY(launch_random_phi(h->stream, h->nnz, K, h->row, h->col, h->data, seed, h->row_offset,
+                                 h->direct_t, freeze ? nullptr : h->direct_b));
+        h->n_launches += 1;
+    } else if (mode == 0) {
+        if (h->opt_variant == 1) {
+            RC_TRY(launch_literal(h->stream, h->nnz, K, h->row, h->col, h->data, h->elog_t, h->elog_b,
+                                  nullptr, h->direct_t, freeze ? nullptr : h->direct_b));
+            h->n_launches += 1;
+        } else {
+            // theta side: cells own, gene panels stream through shared memory
+            SweepArgs A = side_args(h, h->cells);
+            A.own_tab = h->Et;
+            A.oth_tab = h->Eb;
+            A.acc = h->acc_t;
+            A.own_elog = h->elog_t;
+            A.oth_elog = h->elog_b;
+            A.direct = h->direct_t;
+            RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->cells, A));
+            if (!freeze) {
+                // beta side: genes own, cell panels stream
+                SweepArgs B = side_args(h, h->genes);
+                B.own_tab = h->Eb;
+                B.oth_tab = h->Et;
+                B.acc = h->acc_b;
+                B.own_elog = h->elog_b;
+                B.oth_elog = h->elog_t;
+                B.direct = h->direct_b;
+                RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->genes, B));
+            }
+        }
+    }
+    if (!freeze) {
+        // this shard's beta shape sums + column sums of theta.e_x (theta BEFORE its update,
+        // scHPF_.py:701-703) into the exchange buffer
+        RC_TRY(launch_fold(h->stream, h->G, K, h->Eb, h->acc_b, h->direct_b, h->exch));
+        CUDA_TRY(cudaMemcpyAsync(h->exch + (size_t)h->G * K, h->colsum_t_next, sizeof(double) * K,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+        h->n_launches += 1;
+    }
+    return SCHPF_OK;
+}
+
+int step_end_impl(schpf_engine *h, int flags)
+{
+    const bool freeze = flags & SCHPF_FREEZE_GENES;
+    const bool simultaneous = flags & SCHPF_SIMULTANEOUS;
+    const int K = h->K;
+    auto theta_update = [&]() -> int {
+        // scHPF_.py:709-714: theta shape from the row sums, rate from xi (old) + column sums of
+        // beta.e_x, then xi rate; also next iteration's tables and theta.e_x column sums
+        CUDA_TRY(cudaMemsetAsync(h->colsum_t_next, 0, sizeof(double) * K, h->stream));
+        RC_TRY(launch_finalize(h->stream, h->C, K, h->a, h->bp, nullptr, h->Et, h->acc_t, h->direct_t,
+                               h->colsum_b, h->xi_shp, h->xi_rte, h->theta_shp, h->theta_rte, h->elog_t,
+                               h->Et, h->colsum_t_next));
+        h->n_launches += 1;
+        return SCHPF_OK;
+    };
+    auto beta_update = [&]() -> int {
+        // scHPF_.py:699-704
+        CUDA_TRY(cudaMemsetAsync(h->colsum_b, 0, sizeof(double) * K, h->stream));
+        RC_TRY(launch_finalize(h->stream, h->G, K, h->c, h->dp, h->exch, h->Eb, nullptr, nullptr,
+                               h->exch + (size_t)h->G * K, h->eta_shp, h->eta_rte, h->beta_shp, h->beta_rte,
+                               h->elog_b, h->Eb, h->colsum_b));
+        h->n_launches += 1;
+        return SCHPF_OK;
+    };
+    if (simultaneous) {
+        // scHPF_.py:666-684: cell updates see the OLD beta, gene updates the OLD theta
+        RC_TRY(theta_update());
+        if (!freeze) RC_TRY(beta_update());
+    } else {
+        if (!freeze) RC_TRY(beta_update());
+        RC_TRY(theta_update());
+    }
+    h->n_iterations += 1;
+    return SCHPF_OK;
+}
+
+int upload(double *dst, const double *src, int64_t n, cudaStream_t s)
+{
+    CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+    return SCHPF_OK;
+}
+
+int download(double *dst, const double *src, int64_t n, cudaStream_t s)
+{
+    CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    return SCHPF_OK;
+}
+
+int finish_coo(schpf_engine *h)
+{
+    // validate indices, take the data constant sum lgamma(y+1), build both layouts
+    CUDA_TRY(cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream));
+    RC_TRY(launch_validate_coo(h->stream, h->nnz, h->row, h->col, h->data, h->C, h->G, h->flag));
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (flag) {
+        set_error("COO triples out of range:%s%s%s (matrix is %lld x %lld)", (flag & 1) ? " row" : "",
+                  (flag & 2) ? " col" : "", (flag & 4) ? " negative count" : "", (long long)h->C,
+                  (long long)h->G);
+        free_coo(h);
+        return SCHPF_ERR_ARG;
+    }
+    const int ctas = sweep_ctas_per_sm(h->K);
+    int Po = h->opt_panel_rows > 0 ? h->opt_panel_rows : max_panel_rows(h->K, ctas);
+    const int Pmax = max_panel_rows(h->K, 1);
+    if (Po > Pmax) Po = Pmax;
+    Po &= ~3;
+    if (Po < 4) Po = 4;
+    // tables are streamed panel-wise: pad their row counts to whole panels (zero rows)
+    const int64_t C_pad = ((h->C + Po - 1) / Po) * Po, G_pad = ((h->G + Po - 1) / Po) * Po;
+    if (C_pad != h->C_pad || !h->Et) {
+        dev_free(h->Et);
+        RC_TRY(dev_alloc(&h->Et, C_pad * h->ST));
+        h->C_pad = C_pad;
+    }
+    if (G_pad != h->G_pad || !h->Eb) {
+        dev_free(h->Eb);
+        RC_TRY(dev_alloc(&h->Eb, G_pad * h->ST));
+        h->G_pad = G_pad;
+    }
+    CUDA_TRY(cudaMemsetAsync(h->Et, 0, sizeof(double) * (size_t)C_pad * h->ST, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->Eb, 0, sizeof(double) * (size_t)G_pad * h->ST, h->stream));
+    h->tables_t_valid = h->tables_b_valid = false;
+
+    int warps = sweep_default_warps(h->K);
+    if (h->opt_warps > 0 && h->opt_warps < warps) warps = h->opt_warps;
+    RC_TRY(build_side_layout(h->cells, h->stream, h->nnz, h->row, h->col, h->data, h->C, h->G, Po, warps,
+                             h->opt_target_ctas));
+    RC_TRY(build_side_layout(h->genes, h->stream, h->nnz, h->col, h->row, h->data, h->G, h->C, Po, warps,
+                             h->opt_target_ctas));
+
+    int need = h->cells.nblocks * h->cells.nranges;
+    if (need < 1024) need = 1024;
+    if (need > h->partials_cap) {
+        dev_free(h->partials);
+        RC_TRY(dev_alloc(&h->partials, need));
+        h->partials_cap = need;
+    }
+    RC_TRY(launch_lgamma_sum(h->stream, h->nnz, h->data, h->partials, 1024, h->scalars + 1));
+    CUDA_TRY(cudaMemcpyAsync(&h->lgamma_sum, h->scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->have_coo = true;
+    return SCHPF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int schpf_version(void) { return 100; }
+
+const char *schpf_last_error(void) { return g_last_error.c_str(); }
+
+int schpf_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        set_error("cudaGetDeviceCount -> %s", cudaGetErrorString(e));
+        return -SCHPF_ERR_CUDA;
+    }
+    return n;
+}
+
+int schpf_create(schpf_engine_t **out, int device, int64_t ncells, int64_t ngenes, int nfactors, void *stream)
+{
+    if (!out) {
+        set_error("null output handle");
+        return SCHPF_ERR_ARG;
+    }
+    *out = nullptr;
+    if (ncells <= 0 || ngenes <= 0 || nfactors <= 0 || nfactors > SCHPF_MAX_FACTORS) {
+        set_error("bad dimensions: ncells=%lld ngenes=%lld nfactors=%d (1 <= K <= %d)", (long long)ncells,
+                  (long long)ngenes, nfactors, SCHPF_MAX_FACTORS);
+        return SCHPF_ERR_ARG;
+    }
+    if (ncells > 0x7fffffffLL || ngenes > 0x7fffffffLL) {
+        set_error("indices are int32: ncells and ngenes must be < 2^31");
+        return SCHPF_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    schpf_engine *h = new schpf_engine();
+    h->device = device;
+    h->stream = reinterpret_cast<cudaStream_t>(stream);
+    h->C = ncells;
+    h->G = ngenes;
+    h->K = nfactors;
+    h->ST = stride_of_kp(kp_of(nfactors));
+    const int64_t CK = ncells * nfactors, GK = ngenes * nfactors;
+    int rc = SCHPF_OK;
+    auto A = [&](int r) { if (rc == SCHPF_OK) rc = r; };
+    A(dev_alloc(&h->theta_shp, CK));
+    A(dev_alloc(&h->theta_rte, CK));
+    A(dev_alloc(&h->beta_shp, GK));
+    A(dev_alloc(&h->beta_rte, GK));
+    A(dev_alloc(&h->xi_shp, ncells));
+    A(dev_alloc(&h->xi_rte, ncells));
+    A(dev_alloc(&h->eta_shp, ngenes));
+    A(dev_alloc(&h->eta_rte, ngenes));
+    A(dev_alloc(&h->elog_t, CK));
+    A(dev_alloc(&h->elog_b, GK));
+    A(dev_alloc(&h->accum, 2 * CK + 2 * GK));
+    A(dev_alloc(&h->exch, GK + nfactors));
+    A(dev_alloc(&h->colsum_b, (int64_t)nfactors));
+    A(dev_alloc(&h->colsum_t_next, (int64_t)nfactors));
+    A(dev_alloc(&h->scalars, (int64_t)4));
+    A(dev_alloc(&h->slow_hits, (int64_t)1));
+    A(dev_alloc(&h->flag, (int64_t)1));
+    if (rc != SCHPF_OK) {
+        schpf_destroy(h);
+        return rc;
+    }
+    h->acc_t = h->accum;
+    h->direct_t = h->accum + CK;
+    h->acc_b = h->accum + 2 * CK;
+    h->direct_b = h->accum + 2 * CK + GK;
+    cudaMemsetAsync(h->slow_hits, 0, sizeof(unsigned long long), h->stream);
+    cudaMemsetAsync(h->exch, 0, sizeof(double) * (size_t)(GK + nfactors), h->stream);
+    *out = h;
+    return SCHPF_OK;
+}
+
+int schpf_destroy(schpf_engine_t *h)
+{
+    if (!h) return SCHPF_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_coo(h);
+    dev_free(h->theta_shp); dev_free(h->theta_rte); dev_free(h->beta_shp); dev_free(h->beta_rte);
+    dev_free(h->xi_shp); dev_free(h->xi_rte); dev_free(h->eta_shp); dev_free(h->eta_rte);
+    dev_free(h->Et); dev_free(h->Eb); dev_free(h->elog_t); dev_free(h->elog_b);
+    dev_free(h->accum); dev_free(h->exch); dev_free(h->colsum_b); dev_free(h->colsum_t_next);
+    dev_free(h->partials); dev_free(h->scalars); dev_free(h->slow_hits); dev_free(h->flag);
+    for (auto &e : h->ev_pool) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    delete h;
+    return SCHPF_OK;
+}
+
+int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value)
+{
+    RC_TRY(check_handle(h));
+    if (!key) {
+        set_error("null option key");
+        return SCHPF_ERR_ARG;
+    }
+    if (!strcmp(key, "panel_rows")) h->opt_panel_rows = (int)value;
+    else if (!strcmp(key, "warps_per_cta")) h->opt_warps = (int)value;
+    else if (!strcmp(key, "target_ctas")) h->opt_target_ctas = (int)value;
+    else if (!strcmp(key, "variant")) h->opt_variant = (int)value;
+    else if (!strcmp(key, "timing")) h->opt_timing = (int)value;
+    else if (!strcmp(key, "row_offset")) h->row_offset = value;
+    else {
+        set_error("unknown option '%s'", key);
+        return SCHPF_ERR_ARG;
+    }
+    if (h->opt_warps < 0 || h->opt_warps > 12) {
+        set_error("warps_per_cta must be in [0, 12] (0 = automatic)");
+        h->opt_warps = 0;
+        return SCHPF_ERR_ARG;
+    }
+    return SCHPF_OK;
+}
+
+static int set_coo_common(schpf_engine_t *h, const int32_t *row, const int32_t *col, const int32_t *data,
+                          int64_t nnz, cudaMemcpyKind kind)
+{
+    RC_TRY(check_handle(h));
+    if (nnz < 0 || (nnz > 0 && (!row || !col || !data))) {
+        set_error("bad COO arguments (nnz=%lld)", (long long)nnz);
+        return SCHPF_ERR_ARG;
+    }
+    if (nnz > 0x7fffffffLL) {
+        set_error("nnz must be < 2^31 per engine (shard the cells)");
+        return SCHPF_ERR_ARG;
+    }
+    free_coo(h);
+    h->nnz = nnz;
+    RC_TRY(dev_alloc(&h->row, nnz));
+    RC_TRY(dev_alloc(&h->col, nnz));
+    RC_TRY(dev_alloc(&h->data, nnz));
+    if (nnz > 0) {
+        CUDA_TRY(cudaMemcpyAsync(h->row, row, sizeof(int32_t) * nnz, kind, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->col, col, sizeof(int32_t) * nnz, kind, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->data, data, sizeof(int32_t) * nnz, kind, h->stream));
+    }
+    return finish_coo(h);
+}
+
+int schpf_set_coo(schpf_engine_t *h, const int32_t *row, const int32_t *col, const int32_t *data, int64_t nnz)
+{
+    return set_coo_common(h, row, col, data, nnz, cudaMemcpyHostToDevice);
+}
+
+int schpf_set_coo_device(schpf_engine_t *h, const int32_t *d_row, const int32_t *d_col, const int32_t *d_data,
+                         int64_t nnz)
+{
+    return set_coo_common(h, d_row, d_col, d_data, nnz, cudaMemcpyDeviceToDevice);
+}
+
+int schpf_set_hyper(schpf_engine_t *h, double a, double ap, double bp, double c, double cp, double dp)
+{
+    RC_TRY(check_handle(h));
+    if (!(a > 0) || !(ap > 0) || !(bp > 0) || !(c > 0) || !(cp > 0) || !(dp > 0)) {
+        set_error("hyperparameters must be positive: a=%g ap=%g bp=%g c=%g cp=%g dp=%g", a, ap, bp, c, cp, dp);
+        return SCHPF_ERR_ARG;
+    }
+    h->a = a; h->ap = ap; h->bp = bp; h->c = c; h->cp = cp; h->dp = dp;
+    h->have_hyper = true;
+    return SCHPF_OK;
+}
+
+int schpf_set_state(schpf_engine_t *h, const double *theta_shp, const double *theta_rte, const double *beta_shp,
+                    const double *beta_rte, const double *xi_shp, const double *xi_rte, const double *eta_shp,
+                    const double *eta_rte)
+{
+    RC_TRY(check_handle(h));
+    const int64_t CK = h->C * h->K, GK = h->G * h->K;
+    if ((!theta_shp) != (!theta_rte) || (!beta_shp) != (!beta_rte) || (!xi_shp) != (!xi_rte) ||
+        (!eta_shp) != (!eta_rte)) {
+        set_error("shape and rate of a distribution must be given together");
+        return SCHPF_ERR_ARG;
+    }
+    if (theta_shp) {
+        RC_TRY(upload(h->theta_shp, theta_shp, CK, h->stream));
+        RC_TRY(upload(h->theta_rte, theta_rte, CK, h->stream));
+        h->tables_t_valid = false;
+    }
+    if (beta_shp) {
+        RC_TRY(upload(h->beta_shp, beta_shp, GK, h->stream));
+        RC_TRY(upload(h->beta_rte, beta_rte, GK, h->stream));
+        h->tables_b_valid = false;
+    }
+    if (xi_shp) {
+        RC_TRY(upload(h->xi_shp, xi_shp, h->C, h->stream));
+        RC_TRY(upload(h->xi_rte, xi_rte, h->C, h->stream));
+    }
+    if (eta_shp) {
+        RC_TRY(upload(h->eta_shp, eta_shp, h->G, h->stream));
+        RC_TRY(upload(h->eta_rte, eta_rte, h->G, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // host buffers may be reused on return
+    h->have_state = true;
+    return SCHPF_OK;
+}
+
+int schpf_get_state(schpf_engine_t *h, double *theta_shp, double *theta_rte, double *beta_shp, double *beta_rte,
+                    double *xi_shp, double *xi_rte, double *eta_shp, double *eta_rte)
+{
+    RC_TRY(check_handle(h));
+    const int64_t CK = h->C * h->K, GK = h->G * h->K;
+    if (theta_shp) RC_TRY(download(theta_shp, h->theta_shp, CK, h->stream));
+    if (theta_rte) RC_TRY(download(theta_rte, h->theta_rte, CK, h->stream));
+    if (beta_shp) RC_TRY(download(beta_shp, h->beta_shp, GK, h->stream));
+    if (beta_rte) RC_TRY(download(beta_rte, h->beta_rte, GK, h->stream));
+    if (xi_shp) RC_TRY(download(xi_shp, h->xi_shp, h->C, h->stream));
+    if (xi_rte) RC_TRY(download(xi_rte, h->xi_rte, h->C, h->stream));
+    if (eta_shp) RC_TRY(download(eta_shp, h->eta_shp, h->G, h->stream));
+    if (eta_rte) RC_TRY(download(eta_rte, h->eta_rte, h->G, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return SCHPF_OK;
+}
+
+int schpf_step(schpf_engine_t *h, int n_iters, int flags)
+{
+    RC_TRY(check_handle(h));
+    RC_TRY(require_ready(h));
+    for (int t = 0; t < n_iters; ++t) {
+        RC_TRY(step_begin_impl(h, flags, 0, 0));
+        RC_TRY(step_end_impl(h, flags));
+    }
+    return SCHPF_OK;
+}
+
+int schpf_step_with_xphi(schpf_engine_t *h, const double *xphi_host, int flags)
+{
+    RC_TRY(check_handle(h));
+    RC_TRY(require_ready(h));
+    if (!xphi_host && h->nnz > 0) {
+        set_error("null Xphi");
+        return SCHPF_ERR_ARG;
+    }
+    const bool freeze = flags & SCHPF_FREEZE_GENES;
+    double *d_xphi = nullptr;
+    RC_TRY(dev_alloc(&d_xphi, h->nnz * h->K));
+    int rc = upload(d_xphi, xphi_host, h->nnz * h->K, h->stream);
+    if (rc == SCHPF_OK) rc = ensure_tables(h);
+    if (rc == SCHPF_OK) rc = zero_accumulators(h, !freeze);
+    // hpf_numba.py:152-155 for both axes
+    if (rc == SCHPF_OK) rc = launch_scatter_xphi(h->stream, h->nnz, h->K, d_xphi, h->row, h->direct_t);
+    if (rc == SCHPF_OK && !freeze)
+        rc = launch_scatter_xphi(h->stream, h->nnz, h->K, d_xphi, h->col, h->direct_b);
+    if (rc == SCHPF_OK) rc = step_begin_impl(h, flags, 2, 0);
+    if (rc == SCHPF_OK) rc = step_end_impl(h, flags);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_xphi);
+    return rc;
+}
+
+int schpf_step_random_phi(schpf_engine_t *h, uint64_t seed, int flags)
+{
+    RC_TRY(check_handle(h));
+    RC_TRY(require_ready(h));
+    RC_TRY(step_begin_impl(h, flags, 1, seed));
+    return step_end_impl(h, flags);
+}
+
+int schpf_step_begin(schpf_engine_t *h, int flags, int mode, uint64_t seed)
+{
+    RC_TRY(check_handle(h));
+    RC_TRY(require_ready(h));
+    if (mode != 0 && mode != 1) {
+        set_error("schpf_step_begin: mode must be 0 (E-step) or 1 (random phi)");
+        return SCHPF_ERR_ARG;
+    }
+    return step_begin_impl(h, flags, mode, seed);
+}
+
+int schpf_exchange_buffer(schpf_engine_t *h, void **device_ptr, int64_t *n_doubles)
+{
+    RC_TRY(check_handle(h));
+    if (device_ptr) *device_ptr = h->exch;
+    if (n_doubles) *n_doubles = h->G * h->K + h->K;
+    return SCHPF_OK;
+}
+
+int schpf_step_end(schpf_engine_t *h, int flags)
+{
+    RC_TRY(check_handle(h));
+    RC_TRY(require_ready(h));
+    return step_end_impl(h, flags);
+}
+
+int schpf_loss_parts(schpf_engine_t *h, double *sum_llh, int64_t *count)
+{
+    RC_TRY(check_handle(h));
+    RC_TRY(require_ready(h));
+    const int K = h->K;
+    // e_x tables in the sweep layout (hpf_numba.py:33-41); the factored tables are rebuilt afterwards
+    double *Xt = nullptr, *Xb = nullptr;
+    RC_TRY(dev_alloc(&Xt, h->C_pad * h->ST));
+    int rc = dev_alloc(&Xb, h->G_pad * h->ST);
+    if (rc == SCHPF_OK) {
+        cudaMemsetAsync(Xt, 0, sizeof(double) * (size_t)h->C_pad * h->ST, h->stream);
+        cudaMemsetAsync(Xb, 0, sizeof(double) * (size_t)h->G_pad * h->ST, h->stream);
+        rc = launch_ex_table(h->stream, h->C, K, h->theta_shp, h->theta_rte, Xt);
+    }
+    if (rc == SCHPF_OK) rc = launch_ex_table(h->stream, h->G, K, h->beta_shp, h->beta_rte, Xb);
+    double total = 0.0;
+    if (rc == SCHPF_OK) {
+        SweepArgs A = side_args(h, h->cells);
+        A.own_tab = Xt;
+        A.oth_tab = Xb;
+        A.partial = h->partials;
+        rc = timed_sweep(h, SWEEP_LLH, h->cells, A);
+        h->n_launches += 3;
+    }
+    if (rc == SCHPF_OK)
+        rc = launch_sum_partials(h->stream, h->partials, h->cells.nblocks * h->cells.nranges, h->scalars);
+    if (rc == SCHPF_OK) {
+        cudaError_t e = cudaMemcpyAsync(&total, h->scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            set_error("loss read-back -> %s", cudaGetErrorString(e));
+            rc = SCHPF_ERR_CUDA;
+        }
+    } else {
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(Xt);
+    cudaFree(Xb);
+    if (rc != SCHPF_OK) return rc;
+    if (sum_llh) *sum_llh = total - h->lgamma_sum;
+    if (count) *count = h->nnz;
+    return SCHPF_OK;
+}
+
+int schpf_loss(schpf_engine_t *h, double *mean_negative_llh)
+{
+    double s = 0.0;
+    int64_t n = 0;
+    RC_TRY(schpf_loss_parts(h, &s, &n));
+    if (mean_negative_llh) *mean_negative_llh = n > 0 ? -s / (double)n : 0.0;
+    if (n > 0 && !(s == s)) {
+        set_error("non-finite log-likelihood");
+        return SCHPF_ERR_NUMERIC;
+    }
+    return SCHPF_OK;
+}
+
+int schpf_llh_pointwise(schpf_engine_t *h, double *out_host_nnz)
+{
+    RC_TRY(check_handle(h));
+    RC_TRY(require_ready(h));
+    double *d = nullptr;
+    RC_TRY(dev_alloc(&d, h->nnz));
+    int rc = launch_llh_pointwise(h->stream, h->nnz, h->K, h->row, h->col, h->data, h->theta_shp, h->theta_rte,
+                                  h->beta_shp, h->beta_rte, d);
+    if (rc == SCHPF_OK) rc = download(out_host_nnz, d, h->nnz, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    return rc;
+}
+
+int schpf_xphi_debug(schpf_engine_t *h, double *out)
+{
+    RC_TRY(check_handle(h));
+    RC_TRY(require_ready(h));
+    RC_TRY(ensure_tables(h));
+    double *d = nullptr;
+    RC_TRY(dev_alloc(&d, h->nnz * h->K));
+    int rc = launch_literal(h->stream, h->nnz, h->K, h->row, h->col, h->data, h->elog_t, h->elog_b, d, nullptr,
+                            nullptr);
+    if (rc == SCHPF_OK) rc = download(out, d, h->nnz * h->K, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    return rc;
+}
+
+int schpf_synchronize(schpf_engine_t *h)
+{
+    RC_TRY(check_handle(h));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return SCHPF_OK;
+}
+
+int schpf_counter(schpf_engine_t *h, const char *what, double *value)
+{
+    RC_TRY(check_handle(h));
+    if (!what || !value) {
+        set_error("null counter argument");
+        return SCHPF_ERR_ARG;
+    }
+    if (!strcmp(what, "nnz")) *value = (double)h->nnz;
+    else if (!strcmp(what, "padded_nnz_cells")) *value = (double)h->cells.padded_entries;
+    else if (!strcmp(what, "padded_nnz_genes")) *value = (double)h->genes.padded_entries;
+    else if (!strcmp(what, "sweep_launches")) *value = h->n_sweeps;
+    else if (!strcmp(what, "kernel_launches")) *value = h->n_launches;
+    else if (!strcmp(what, "iterations")) *value = h->n_iterations;
+    else if (!strcmp(what, "layout_bytes")) *value = (double)(h->cells.bytes + h->genes.bytes);
+    else if (!strcmp(what, "panel_rows")) *value = (double)h->cells.panel_rows;
+    else if (!strcmp(what, "grid_cells")) *value = (double)h->cells.nblocks * h->cells.nranges;
+    else if (!strcmp(what, "grid_genes")) *value = (double)h->genes.nblocks * h->genes.nranges;
+    else if (!strcmp(what, "sweep_ms")) {
+        RC_TRY(collect_timing(h));
+        *value = h->sweep_ms_accum;
+    } else if (!strcmp(what, "reset")) {
+        RC_TRY(collect_timing(h));
+        h->sweep_ms_accum = 0.0;
+        h->n_sweeps = h->n_launches = h->n_iterations = 0;
+        *value = 0.0;
+    } else if (!strcmp(what, "slow_path_hits")) {
+        unsigned long long v = 0;
+        CUDA_TRY(cudaMemcpyAsync(&v, h->slow_hits, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        *value = (double)v;
+    } else {
+        set_error("unknown counter '%s'", what);
+        return SCHPF_ERR_ARG;
+    }
+    return SCHPF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,265 @@
+// The hot kernel: one "sweep" over all nonzeros of the count matrix.
+//
+// Replaces, per CAVI iteration, the reference's compute_Xphi_data
+// (hpf_numba.py:55-114) fused with ONE of its two compute_loading_shape_update
+// scatters (hpf_numba.py:129-156): the cells-own sweep produces the theta shape
+// sums, the genes-own sweep the beta shape sums.  The (nnz x K) Xphi array of
+// the reference is never materialised.  In SWEEP_LLH mode the same traversal
+// evaluates compute_pois_llh (hpf_numba.py:25-51) summed over nonzeros.
+//
+// Maths: with Elog = psi(shape) - log(rate) and the factored
+// tables Et[c,k] = exp(Elog_t[c,k] - max_k), Eb[g,k] likewise,
+//     phi_ik = Et[c,k] Eb[g,k] / s_i,   s_i = sum_k Et[c,k] Eb[g,k]
+// which is the reference's softmax (:98-112) with the max subtraction moved
+// out of the per-nonzero loop.  For an OWNER row o and its nonzeros i
+//     sum_i y_i phi_ik = E_own[o,k] * sum_i (y_i / s_i) E_oth[oth_i, k]
+// so a lane keeps E_own[o,:] and the running sum in registers, streams the
+// OTHER side's rows out of a shared-memory panel, and needs no atomics per
+// nonzero.  If s_i underflows (rows whose maxima sit on different factors by
+// > ~640 nats) the nonzero is redone in log space exactly as the reference
+// does and added to a separate `direct` accumulator.
+//
+// Mapping (B200): a CTA owns W*16 owners (one per lane PAIR; lane h of a pair
+// holds the 16-byte units {2j+h} of the K-row), walks a range of panels of the
+// other axis; each panel is brought into shared memory with one 1-D bulk
+// async copy (cp.async.bulk -> UBLKCP) completing on an mbarrier; the entry
+// stream is a per-(warp, panel) sliced-ELL block, two steps per 128-bit load.
+#include "common.cuh"
+
+namespace schpf {
+
+namespace {
+
+constexpr int SWEEP_MAX_WARPS = 12;
+
+// A lane keeps 3*KP/2 doubles live (owner row, accumulators, streamed row) plus
+// ~44 registers of addressing: the CTA shape is picked per KP so that this fits
+// the register file without spilling (ptxas -v is checked in DESIGN.md §4).
+__host__ __device__ constexpr int sweep_min_ctas(int KP) { return KP <= 32 ? 2 : 1; }
+__host__ __device__ constexpr int sweep_max_warps(int KP)
+{
+    // registers are granted per SM sub-partition (16384 each): what counts is warps per
+    // sub-partition, so CTA sizes are multiples of 4 warps where the budget is tight
+    return KP <= 16 ? 10 : KP <= 28 ? 8 : KP <= 32 ? 6 : KP <= 40 ? 12 : 8;
+}
+
+template <int KP>
+struct SweepCfg {
+    static constexpr int ST = stride_of_kp(KP);
+    static constexpr int U = KP / 4;      // 16-byte units per lane
+    static constexpr int D = KP / 2;      // doubles per lane
+    static constexpr int MIN_CTAS = sweep_min_ctas(KP);
+    static constexpr int MAX_WARPS = sweep_max_warps(KP);
+};
+
+template <int KP, int MODE>
+__global__ void __launch_bounds__(SweepCfg<KP>::MAX_WARPS * 32, SweepCfg<KP>::MIN_CTAS)
+sweep_kernel(const SweepArgs A)
+{
+    using Cfg = SweepCfg<KP>;
+    constexpr int ST = Cfg::ST, U = Cfg::U, D = Cfg::D;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *panel = reinterpret_cast<double *>(smem_raw);
+    const uint32_t panel_bytes = (uint32_t)A.panel_rows * ST * 8u;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + panel_bytes);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = lane >> 1, h = lane & 1;
+    const int b = blockIdx.x / A.nranges, r = blockIdx.x - b * A.nranges;
+    const int p0 = r * A.panels_per_range;
+    const int p1 = min(p0 + A.panels_per_range, A.npanel);
+    const int wg = b * A.warps + warp;                       // global warp index
+    const int own = A.own_id[(int64_t)wg * GROUPS_PER_WARP + q];
+
+    double a[D], acc[D];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        double2 v = make_double2(0.0, 0.0);
+        if (own >= 0) v = reinterpret_cast<const double2 *>(A.own_tab + (int64_t)own * ST)[2 * j + h];
+        a[2 * j] = v.x;
+        a[2 * j + 1] = v.y;
+        acc[2 * j] = 0.0;
+        acc[2 * j + 1] = 0.0;
+    }
+    double llh = 0.0;
+
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint32_t parity = 0;
+    const int64_t *sp = A.seg_ptr + (int64_t)wg * (A.npanel + 1);
+
+    for (int p = p0; p < p1; ++p) {
+        if (p > p0) __syncthreads();     // every warp is done with the previous panel
+        if (tid == 0) {
+            mbar_expect_tx(mbar, panel_bytes);
+            bulk_g2s(panel, A.oth_tab + (int64_t)p * A.panel_rows * ST, panel_bytes, mbar);
+        }
+        const int64_t i0 = sp[p], i1 = sp[p + 1];
+        const int4 *ep = A.entries + i0 * GROUPS_PER_WARP + q;
+        int4 cur = make_int4(0, 0, 0, 0);
+        if (i0 < i1) cur = ld_stream_int4(ep);
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+
+        for (int64_t i = i0; i < i1; ++i) {
+            ep += GROUPS_PER_WARP;
+            int4 nxt = cur;
+            if (i + 1 < i1) nxt = ld_stream_int4(ep);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int ex = half ? cur.z : cur.x;
+                const int ey = half ? cur.w : cur.y;
+                const int t = ex & 0x7fffffff;
+                const double2 *rp = reinterpret_cast<const double2 *>(panel) + (t * (ST / 2) + h);
+                double bv[D];
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const double2 v = rp[2 * j];
+                    bv[2 * j] = v.x;
+                    bv[2 * j + 1] = v.y;
+                }
+                double s = a[0] * bv[0];
+#pragma unroll
+                for (int k = 1; k < D; ++k) s = fma(a[k], bv[k], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                const double y = (double)ey;
+                if (MODE == SWEEP_SHAPE) {
+                    const bool ok = s > TINY_NORMALIZER;
+                    const double w = ok ? div_pos(y, s) : 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) acc[k] = fma(w, bv[k], acc[k]);
+                    if (!ok && ey != 0 && own >= 0) {
+                        // log-space redo of this nonzero (hpf_numba.py:98-112); both lanes of the pair
+                        // get here together.  Rare: kept rolled so it costs the hot path no registers.
+                        const int K = A.K;
+                        const double *eo = A.own_elog + (int64_t)own * K;
+                        const double *et = A.oth_elog + ((int64_t)p * A.panel_rows + t) * K;
+                        double largest = -INFINITY, normalizer = 0.0;
+#pragma unroll 1
+                        for (int k = 0; k < K; ++k) largest = fmax(largest, eo[k] + et[k]);
+#pragma unroll 1
+                        for (int k = 0; k < K; ++k) normalizer += exp(eo[k] + et[k] - largest);
+#pragma unroll 1
+                        for (int k = 2 * h; k < K; k += 4) {
+                            atomicAdd(A.direct + (int64_t)own * K + k, y * exp(eo[k] + et[k] - largest) / normalizer);
+                            if (k + 1 < K)
+                                atomicAdd(A.direct + (int64_t)own * K + k + 1,
+                                          y * exp(eo[k + 1] + et[k + 1] - largest) / normalizer);
+                        }
+                        if (h == 0) atomicAdd(A.slow_hits, 1ULL);
+                    }
+                } else {
+                    // hpf_numba.py:49-50 without the lgamma term (a constant of the data)
+                    const double v = fma(y, log(s), -s);
+                    if (ex >= 0 && h == 0) llh += v;
+                }
+            }
+            cur = nxt;
+        }
+    }
+
+    if (MODE == SWEEP_SHAPE) {
+        if (own >= 0) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    const int k = 4 * j + 2 * h + d;
+                    if (k < A.K) atomicAdd(A.acc + (int64_t)own * A.K + k, acc[2 * j + d]);
+                }
+            }
+        }
+    } else {
+        __shared__ double red[SWEEP_MAX_WARPS];
+        llh = warp_sum(llh);
+        if (lane == 0) red[warp] = llh;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < A.warps; ++w) t += red[w];
+            A.partial[blockIdx.x] = t;
+        }
+    }
+}
+
+template <int KP, int MODE>
+int launch_one(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
+{
+    const size_t smem = (size_t)L.panel_rows * SweepCfg<KP>::ST * 8 + 16;
+    static bool configured = false;   // per instantiation
+    static size_t configured_smem = 0;
+    if (!configured || smem > configured_smem) {
+        CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<KP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<KP, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        configured = true;
+        configured_smem = smem;
+    }
+    const int grid = L.nblocks * L.nranges;
+    if (grid <= 0) return SCHPF_OK;
+    sweep_kernel<KP, MODE><<<grid, L.warps * 32, smem, stream>>>(args);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("sweep_kernel<KP=%d,mode=%d> launch (grid %d, block %d, smem %zu) -> %s", KP, MODE, grid,
+                  L.warps * 32, smem, cudaGetErrorString(e));
+        return SCHPF_ERR_CUDA;
+    }
+    return SCHPF_OK;
+}
+
+template <int MODE>
+int dispatch_kp(int KP, const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
+{
+    switch (KP) {
+#define CASE_KP(v) \
+    case v: return launch_one<v, MODE>(L, args, stream);
+        CASE_KP(4) CASE_KP(8) CASE_KP(12) CASE_KP(16) CASE_KP(20) CASE_KP(24) CASE_KP(28) CASE_KP(32)
+        CASE_KP(36) CASE_KP(40) CASE_KP(44) CASE_KP(48) CASE_KP(52) CASE_KP(56) CASE_KP(60) CASE_KP(64)
+#undef CASE_KP
+        default:
+            set_error("nfactors padded to %d is outside the instantiated range (K <= %d)", KP,
+                      SCHPF_MAX_FACTORS);
+            return SCHPF_ERR_ARG;
+    }
+}
+
+}  // namespace
+
+size_t sweep_smem_bytes(int K, int panel_rows)
+{
+    return (size_t)panel_rows * stride_of_kp(kp_of(K)) * 8 + 16;
+}
+
+// Largest panel (rows of the other axis) such that `ctas_per_sm` CTAs fit in the
+// 227 KB of shared memory an SM can give (1 KB per CTA is reserved by the system).
+int max_panel_rows(int K, int ctas_per_sm)
+{
+    const int ST = stride_of_kp(kp_of(K));
+    const size_t per_cta = (size_t)(228 * 1024) / ctas_per_sm - 1024 - 64;
+    int rows = (int)(per_cta / ((size_t)ST * 8));
+    rows &= ~3;
+    if (rows > 4096) rows = 4096;   // 12-bit local index in the sort key
+    return rows;
+}
+
+int sweep_ctas_per_sm(int K) { return sweep_min_ctas(kp_of(K)); }
+int sweep_default_warps(int K) { return sweep_max_warps(kp_of(K)); }
+
+int launch_sweep(int mode, int K, const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
+{
+    const int KP = kp_of(K);
+    if (L.warps > sweep_max_warps(KP) || L.warps < 1) {
+        set_error("warps_per_cta must be in [1, %d] for K=%d", sweep_max_warps(KP), K);
+        return SCHPF_ERR_ARG;
+    }
+    if (mode == SWEEP_SHAPE) return dispatch_kp<SWEEP_SHAPE>(KP, L, args, stream);
+    return dispatch_kp<SWEEP_LLH>(KP, L, args, stream);
+}
+
+}  // namespace schpf

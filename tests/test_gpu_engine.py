@@ -1,0 +1,330 @@
+"""GPU parity, engine level: whole CAVI iterations on the device (C ABI engine,
+called through schpf_b200.engine / the scHPF estimator) against golden runs of
+the reference and against the oracle.
+
+Tolerances: BASELINE.json asks for theta/beta within 1e-6 relative of the
+reference after 50 iterations; what is asserted here is 1e-9 (measured ~1e-12:
+only summation order and 1-ulp libm differences remain).  Index handling
+(layout, permutations, padding) is covered by exact integer-valued checks.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_equal
+from scipy.sparse import coo_matrix
+
+from schpf_b200 import scHPF, HPF_Gamma
+from schpf_b200.engine import CaviEngine
+from schpf_b200.synth import synth_coo
+from conftest import max_rel
+from oracle import hpf_c as oc
+from oracle import hpf_numpy as onp
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ("theta", "beta", "xi", "eta")
+TOL = 1e-9
+
+
+def _X(g):
+    return coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(int(v) for v in g["shape"]))
+
+
+def _pairs(g, prefix):
+    return {n: (g[prefix + n + "_shp"], g[prefix + n + "_rte"]) for n in NAMES}
+
+
+def _engine_from(g, prefix, K, **opts):
+    C, G = (int(v) for v in g["shape"])
+    e = CaviEngine(C, G, K, **opts)
+    e.set_coo(g["row"], g["col"], g["data"])
+    e.set_hyper(*[float(g[k]) for k in ("a", "ap", "bp", "c", "cp", "dp")])
+    e.set_state(**_pairs(g, prefix))
+    return e
+
+
+def _prep_capacity_shapes(g, prefix, K):
+    """what _fit does before the loop (scHPF_.py:614-618)"""
+    out = {k: v.copy() for k, v in g.items()}
+    out[prefix + "xi_shp"] = np.full_like(g[prefix + "xi_shp"], float(g["ap"]) + K * float(g["a"]))
+    out[prefix + "eta_shp"] = np.full_like(g[prefix + "eta_shp"], float(g["cp"]) + K * float(g["c"]))
+    return out
+
+
+def _check_state(e, g, prefix, tol=TOL):
+    st = e.get_state()
+    for n in NAMES:
+        assert max_rel(st[n][0], g[prefix + n + "_shp"]) < tol, n + " shape"
+        assert max_rel(st[n][1], g[prefix + n + "_rte"]) < tol, n + " rate"
+
+
+# ------------------------------------------------------------ golden runs ----
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n", [1, 10, 50])
+def test_engine_iterations_match_reference(g_cavi, n, variant):
+    g = _prep_capacity_shapes(g_cavi, "init_", 5)
+    with _engine_from(g, "init_", 5, variant=variant) as e:
+        cf = int(g["it%d_check_freq" % n])
+        loss = []
+        for t in range(n):
+            e.step(1)
+            if t % cf == 0:
+                loss.append(e.loss())
+        _check_state(e, g, "it%d_" % n)
+        assert_allclose(loss, g["it%d_loss" % n], rtol=1e-11)
+        assert e.counter("slow_path_hits") == 0
+
+
+@pytest.mark.parametrize("panel_rows,warps,target", [(64, 2, 64), (256, 8, 4000), (4, 1, 1)])
+def test_engine_layout_variants_agree(g_cavi, panel_rows, warps, target):
+    """Multiple panels / ranges / CTA shapes: same numbers whatever the tiling."""
+    g = _prep_capacity_shapes(g_cavi, "init_", 5)
+    with _engine_from(g, "init_", 5, panel_rows=panel_rows, warps_per_cta=warps, target_ctas=target) as e:
+        assert e.counter("panel_rows") == panel_rows
+        e.step(10)
+        _check_state(e, g, "it10_")
+        assert_allclose(e.loss(), g["it10_loss"][-1], rtol=1e-11)
+
+
+def test_estimator_fit_matches_reference(g_cavi):
+    g, X = g_cavi, _X(g_cavi)
+    gam = lambda n: HPF_Gamma(g["init_" + n + "_shp"].copy(), g["init_" + n + "_rte"].copy())
+    m = scHPF(5, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]),
+              xi=gam("xi"), theta=gam("theta"), eta=gam("eta"), beta=gam("beta"))
+    m.fit(X, reinit=False, min_iter=50, max_iter=50, check_freq=10)
+    for n in NAMES:
+        assert max_rel(getattr(m, n).vi_shape, g["it50_" + n + "_shp"]) < TOL
+        assert max_rel(getattr(m, n).vi_rate, g["it50_" + n + "_rte"]) < TOL
+    assert_allclose(m.loss, g["it50_loss"], rtol=1e-11)
+    assert_allclose(m.mean_negative_pois_llh(X), g["it50_loss"][-1], rtol=1e-10)
+
+
+def test_estimator_reinit_and_project_match_seeded_reference(g_reinit, g_cavi, g_project):
+    g, X = g_reinit, _X(g_reinit)
+    np.random.seed(int(g["seed"]))
+    m = scHPF(3, verbose=False).fit(X, min_iter=6, max_iter=6, check_freq=2)   # t==0 Dirichlet branch
+    for n in NAMES:
+        assert max_rel(getattr(m, n).vi_shape, g[n + "_shp"]) < TOL
+        assert max_rel(getattr(m, n).vi_rate, g[n + "_rte"]) < TOL
+    assert_allclose(m.loss, g["loss"], rtol=1e-11)
+
+    c, p = g_cavi, g_project
+    gam = lambda n: HPF_Gamma(c["it50_" + n + "_shp"].copy(), c["it50_" + n + "_rte"].copy())
+    trained = scHPF(5, verbose=False, bp=float(c["bp"]), dp=float(c["dp"]),
+                    xi=gam("xi"), theta=gam("theta"), eta=gam("eta"), beta=gam("beta"))
+    np.random.seed(int(p["seed"]))
+    proj = trained.project(_X(p), min_iter=10, max_iter=10, check_freq=2)
+    assert proj.eta == trained.eta and proj.beta == trained.beta
+    assert max_rel(proj.theta.vi_shape, p["theta_shp"]) < TOL
+    assert max_rel(proj.theta.vi_rate, p["theta_rte"]) < TOL
+    assert max_rel(proj.xi.vi_rate, p["xi_rte"]) < TOL
+    assert_allclose(proj.loss, p["loss"], rtol=1e-11)
+    assert_allclose(proj.cell_score(), p["cell_score"], rtol=1e-9)
+
+
+def test_simultaneous_matches_reference(g_simul):
+    g = _prep_capacity_shapes(g_simul, "init_", 3)
+    with _engine_from(g, "init_", 3) as e:
+        e.step(7, simultaneous=True)
+        _check_state(e, g, "fin_")
+        assert_allclose(e.loss(), g["loss"][-1], rtol=1e-11)
+
+
+# ------------------------------------------------ oracle on seeded inputs ----
+def _random_problem(C, G, K, nnz, seed, zeros=False):
+    rng = np.random.default_rng(seed)
+    row = rng.integers(0, C, nnz).astype(np.int32)
+    col = rng.integers(0, G, nnz).astype(np.int32)
+    data = rng.integers(0 if zeros else 1, 30, nnz).astype(np.int32)
+    st = onp.State(rng.uniform(0.15, 0.45, (C, K)), rng.uniform(0.5, 1.5, (C, K)),
+                   rng.uniform(0.15, 0.45, (G, K)), rng.uniform(0.5, 1.5, (G, K)),
+                   np.full(C, 1.0 + K * 0.3), rng.uniform(0.5, 1.5, C),
+                   np.full(G, 1.0 + K * 0.3), rng.uniform(0.5, 1.5, G))
+    return row, col, data, st
+
+
+def _run_pair(C, G, K, nnz, seed, n_iter, freeze=False, zeros=False, **opts):
+    row, col, data, st = _random_problem(C, G, K, nnz, seed, zeros)
+    hyp = (0.3, 1.0, 0.7, 0.3, 1.0, 1.3)
+    with CaviEngine(C, G, K, **opts) as e:
+        e.set_coo(row, col, data)
+        e.set_hyper(*hyp)
+        e.set_state(theta=(st.theta_shp, st.theta_rte), beta=(st.beta_shp, st.beta_rte),
+                    xi=(st.xi_shp, st.xi_rte), eta=(st.eta_shp, st.eta_rte))
+        e.step(n_iter, freeze_genes=freeze)
+        got = e.get_state()
+        got_loss = e.loss()
+        got_llh = e.llh_pointwise()
+        got_xphi = e.xphi() if nnz * K < 2_000_000 else None
+        hits = e.counter("slow_path_hits")
+    want_loss = oc.cavi_run(data, row, col, st, *hyp, n_iter, freeze_genes=freeze, check_freq=0)
+    return got, got_loss, got_llh, got_xphi, st, (row, col, data), hits
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 5, 7, 10, 15, 16, 20, 24, 30, 32, 33, 40, 50, 64])
+def test_every_instantiated_K_against_oracle(K):
+    # ragged: duplicates, empty cells and genes (nnz << C*G), explicit zeros
+    got, loss, llh, xphi, st, (row, col, data), hits = _run_pair(301, 173, K, 4000, K, 5, zeros=True,
+                                                                  panel_rows=64)
+    assert max_rel(got["theta"][0], st.theta_shp) < TOL and max_rel(got["theta"][1], st.theta_rte) < TOL
+    assert max_rel(got["beta"][0], st.beta_shp) < TOL and max_rel(got["beta"][1], st.beta_rte) < TOL
+    assert max_rel(got["xi"][1], st.xi_rte) < TOL and max_rel(got["eta"][1], st.eta_rte) < TOL
+    want_llh = oc.compute_pois_llh(data, row, col, st.theta_shp, st.theta_rte, st.beta_shp, st.beta_rte)
+    assert_allclose(llh, want_llh, rtol=1e-9, atol=1e-12)
+    assert_allclose(loss, np.mean(-want_llh), rtol=1e-11)
+    assert_allclose(xphi, oc.compute_Xphi_data(data, row, col, st.theta_shp, st.theta_rte,
+                                               st.beta_shp, st.beta_rte), rtol=1e-9, atol=0)
+    assert hits == 0
+
+
+def test_frozen_genes_leave_beta_eta_bit_identical():
+    row, col, data, st = _random_problem(500, 300, 8, 20000, 3)
+    with CaviEngine(500, 300, 8) as e:
+        e.set_coo(row, col, data)
+        e.set_hyper(0.3, 1.0, 0.7, 0.3, 1.0, 1.3)
+        e.set_state(theta=(st.theta_shp, st.theta_rte), beta=(st.beta_shp, st.beta_rte),
+                    xi=(st.xi_shp, st.xi_rte), eta=(st.eta_shp, st.eta_rte))
+        e.step(4, freeze_genes=True)
+        got = e.get_state()
+    assert_equal(got["beta"][0], st.beta_shp)
+    assert_equal(got["beta"][1], st.beta_rte)
+    assert_equal(got["eta"][1], st.eta_rte)
+    oc.cavi_run(data, row, col, st, 0.3, 1.0, 0.7, 0.3, 1.0, 1.3, 4, freeze_genes=True)
+    assert max_rel(got["theta"][0], st.theta_shp) < TOL and max_rel(got["xi"][1], st.xi_rte) < TOL
+
+
+def test_edge_shapes():
+    # one cell, one gene, one nonzero; and a matrix whose last cell / gene are empty
+    for C, G, K, nnz in ((1, 1, 3, 1), (2, 5, 4, 3), (40, 3, 2, 60), (3, 700, 6, 500)):
+        got, loss, llh, xphi, st, coo, hits = _run_pair(C, G, K, nnz, C * 7 + G, 3)
+        assert max_rel(got["theta"][0], st.theta_shp) < TOL
+        assert max_rel(got["beta"][0], st.beta_shp) < TOL
+        assert np.isfinite(loss)
+    # empty matrix: every shape falls back to its prior, rates still move
+    C, G, K = 6, 4, 3
+    row, col, data, st = _random_problem(C, G, K, 0, 1)
+    with CaviEngine(C, G, K) as e:
+        e.set_coo(row, col, data)
+        e.set_hyper(0.3, 1.0, 0.7, 0.25, 1.0, 1.3)
+        e.set_state(theta=(st.theta_shp, st.theta_rte), beta=(st.beta_shp, st.beta_rte),
+                    xi=(st.xi_shp, st.xi_rte), eta=(st.eta_shp, st.eta_rte))
+        e.step(2)
+        got = e.get_state()
+    assert_equal(got["theta"][0], np.full((C, K), 0.3))
+    assert_equal(got["beta"][0], np.full((G, K), 0.25))
+
+
+def test_input_order_and_determinism():
+    """The layout is a pure function of the multiset of triples: permuting the COO
+    arrays changes nothing beyond the order of atomic adds."""
+    row, col, data, st = _random_problem(400, 900, 20, 30000, 11)
+    perm = np.random.default_rng(5).permutation(row.shape[0])
+    res = []
+    for r, c, d in ((row, col, data), (row[perm], col[perm], data[perm]), (row, col, data)):
+        with CaviEngine(400, 900, 20, panel_rows=128) as e:
+            e.set_coo(r, c, d)
+            e.set_hyper(0.3, 1.0, 0.7, 0.3, 1.0, 1.3)
+            e.set_state(theta=(st.theta_shp, st.theta_rte), beta=(st.beta_shp, st.beta_rte),
+                        xi=(st.xi_shp, st.xi_rte), eta=(st.eta_shp, st.eta_rte))
+            e.step(5)
+            res.append((e.get_state(), e.loss(), e.counter("padded_nnz_cells")))
+    for other in res[1:]:
+        assert other[2] == res[0][2]                       # integer layout identical
+        assert max_rel(other[0]["theta"][0], res[0][0]["theta"][0]) < 1e-12
+        assert max_rel(other[0]["beta"][0], res[0][0]["beta"][0]) < 1e-12
+        assert_allclose(other[1], res[0][1], rtol=1e-13)
+
+
+def test_underflow_fallback_matches_reference_arithmetic():
+    """Rows whose Elog maxima sit on different factors by more than ~640 nats make the
+    factored softmax underflow; those nonzeros are redone in log space like the reference."""
+    C, G, K = 64, 48, 4
+    rng = np.random.default_rng(2)
+    row = np.repeat(np.arange(C, dtype=np.int32), 6)
+    col = rng.integers(0, G, row.shape[0]).astype(np.int32)
+    data = rng.integers(1, 9, row.shape[0]).astype(np.int32)
+    ts = np.full((C, K), 1e-3); ts[np.arange(C), np.arange(C) % K] = 50.0     # psi(1e-3) ~ -1000
+    bs = np.full((G, K), 1e-3); bs[np.arange(G), (np.arange(G) + 1) % K] = 50.0
+    st = onp.State(ts, np.ones((C, K)), bs, np.ones((G, K)), np.full(C, 1.0), np.ones(C), np.full(G, 1.0), np.ones(G))
+    hyp = (1e-3, 1.0, 0.7, 1e-3, 1.0, 1.3)
+    with CaviEngine(C, G, K) as e:
+        e.set_coo(row, col, data)
+        e.set_hyper(*hyp)
+        e.set_state(theta=(st.theta_shp, st.theta_rte), beta=(st.beta_shp, st.beta_rte),
+                    xi=(st.xi_shp, st.xi_rte), eta=(st.eta_shp, st.eta_rte))
+        xphi = e.xphi()
+        e.step(1)
+        got = e.get_state()
+        hits = e.counter("slow_path_hits")
+    assert hits > 0
+    want_xphi = onp.compute_Xphi_data(data, row, col, st.theta_shp, st.theta_rte, st.beta_shp, st.beta_rte)
+    assert_allclose(xphi, want_xphi, rtol=1e-9, atol=1e-300)
+    onp.cavi_iteration(data, row, col, st, hyp[0], hyp[2], hyp[3], hyp[5])
+    assert max_rel(got["theta"][0], st.theta_shp) < 1e-9
+    assert max_rel(got["beta"][0], st.beta_shp) < 1e-9
+    assert np.all(np.isfinite(got["theta"][0])) and np.all(np.isfinite(got["beta"][1]))
+
+
+def test_random_phi_device_draw_is_a_valid_first_iteration():
+    row, col, data, st = _random_problem(300, 200, 7, 15000, 4)
+    outs = []
+    for seed in (123, 123, 124):
+        with CaviEngine(300, 200, 7) as e:
+            e.set_coo(row, col, data)
+            e.set_hyper(0.3, 1.0, 0.7, 0.3, 1.0, 1.3)
+            e.set_state(theta=(st.theta_shp, st.theta_rte), beta=(st.beta_shp, st.beta_rte),
+                        xi=(st.xi_shp, st.xi_rte), eta=(st.eta_shp, st.eta_rte))
+            e.step_random_phi(seed)
+            outs.append(e.get_state())
+    th = outs[0]["theta"][0]
+    # y * Dirichlet sums to y: total mass is conserved on both sides, exactly as for the E-step
+    assert_allclose((th - 0.3).sum(), data.sum(), rtol=1e-12)
+    assert_allclose((outs[0]["beta"][0] - 0.3).sum(), data.sum(), rtol=1e-12)
+    assert max_rel(outs[1]["theta"][0], th) < 1e-12            # same seed -> same draw
+    assert np.abs(outs[2]["theta"][0] - th).max() > 1e-3        # different seed -> different draw
+    # Dirichlet(1_K) marginals: E[phi_k] = 1/K
+    per_factor = (th - 0.3).sum(0) / data.sum()
+    assert np.abs(per_factor - 1 / 7).max() < 0.01
+
+
+def test_error_paths():
+    from schpf_b200._lib import SchpfError
+    with pytest.raises(SchpfError):
+        CaviEngine(10, 10, 65)
+    with CaviEngine(4, 4, 2) as e:
+        with pytest.raises(SchpfError):
+            e.step(1)                                           # nothing set yet
+        with pytest.raises(SchpfError):
+            e.set_coo(np.array([4], np.int32), np.array([0], np.int32), np.array([1], np.int32))
+        with pytest.raises(SchpfError):
+            e.set_hyper(0.3, 1.0, -1.0, 0.3, 1.0, 1.0)
+        with pytest.raises(ValueError):
+            e.set_state(theta=(np.ones((3, 2)), np.ones((3, 2))))
+
+
+# ---------------------------------- size-independent properties, full size ---
+def test_full_size_properties():
+    """BASELINE cfg-2 shape scaled to fit the test budget (50k x 20k, ~300 nnz/cell, K=20):
+    mass conservation, tiled sweep == literal per-nonzero kernel, loss identity."""
+    C, G, K = 50000, 20000, 20
+    X = synth_coo(C, G, 300, K, seed=3)
+    rng = np.random.default_rng(0)
+    st = {"theta": (rng.uniform(0.15, 0.45, (C, K)), rng.uniform(0.5, 1.5, (C, K))),
+          "beta": (rng.uniform(0.15, 0.45, (G, K)), rng.uniform(0.5, 1.5, (G, K))),
+          "xi": (np.full(C, 7.0), rng.uniform(0.5, 1.5, C)), "eta": (np.full(G, 7.0), rng.uniform(0.5, 1.5, G))}
+    out = []
+    for variant in (0, 1):
+        with CaviEngine(C, G, K, variant=variant) as e:
+            e.set_coo(X.row, X.col, X.data)
+            e.set_hyper(0.3, 1.0, 0.05, 0.3, 1.0, 0.02)
+            e.set_state(**st)
+            e.step(3)
+            out.append((e.get_state(), e.loss(), e.llh_pointwise(), e.counter("slow_path_hits")))
+    (s0, l0, p0, h0), (s1, l1, p1, h1) = out
+    total = float(X.data.sum())
+    assert_allclose((s0["theta"][0] - 0.3).sum(), total, rtol=1e-11)     # sum_k phi = 1
+    assert_allclose((s0["beta"][0] - 0.3).sum(), total, rtol=1e-11)
+    for n in NAMES:
+        assert max_rel(s0[n][0], s1[n][0]) < 1e-10 and max_rel(s0[n][1], s1[n][1]) < 1e-10
+    assert_allclose(l0, np.mean(-p0), rtol=1e-12)                        # sweep llh == pointwise llh
+    assert_allclose(l0, l1, rtol=1e-12)
+    assert h0 == 0

@@ -1,0 +1,235 @@
+"""CPU-only tests: the C ABI exports what include/schpf_b200.h declares, the
+product path refuses to run without a GPU, and the host logic of the estimator
+(setup, RNG order, loop schedule, convergence rules, error behaviour) reproduces
+golden runs of the reference when its engine is swapped for the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_equal
+from scipy.sparse import coo_matrix
+
+import schpf_b200
+from schpf_b200 import _lib, scHPF, HPF_Gamma, combine_across_cells
+from schpf_b200 import scHPF_ as shell
+from schpf_b200.engine import shard_bounds_by_nnz
+from conftest import ROOT, has_cuda, max_rel
+from oracle_engine import OracleEngine
+
+STATE = ("theta_shp", "theta_rte", "beta_shp", "beta_rte", "xi_shp", "xi_rte", "eta_shp", "eta_rte")
+
+
+def _X(g):
+    return coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(int(v) for v in g["shape"]))
+
+
+def _gam(g, name, prefix=""):
+    return HPF_Gamma(g[prefix + name + "_shp"].copy(), g[prefix + name + "_rte"].copy())
+
+
+@pytest.fixture()
+def oracle_backend(monkeypatch):
+    monkeypatch.setattr(shell, "_engine_factory", OracleEngine)
+
+
+# ---------------------------------------------------------------- C ABI ------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "schpf_b200.h")).read()
+    declared = set(re.findall(r"\b(schpf_[a-zA-Z_]+)\s*\(", header))
+    declared.discard("schpf_engine")
+    assert len(declared) >= 28
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export: " + name
+    assert set(_lib.SIGNATURES) == declared
+    assert _lib.load().schpf_version() >= 100
+
+
+@pytest.mark.skipif(has_cuda(), reason="checks the no-GPU behaviour")
+def test_product_path_fails_loudly_without_gpu():
+    from schpf_b200 import hpf_cuda
+    with pytest.raises(_lib.SchpfError):
+        hpf_cuda.psi(np.array([1.0, 2.0]))
+    X = coo_matrix((np.array([1, 2], dtype=np.int32), (np.array([0, 1]), np.array([1, 0]))), shape=(2, 2))
+    with pytest.raises(_lib.SchpfError):
+        scHPF(2, verbose=False).fit(X, max_iter=1)
+
+
+# ------------------------------------------------------- estimator shell -----
+def test_setup_matches_reference_rng_and_hypers(g_cavi):
+    g, X = g_cavi, _X(g_cavi)
+    np.random.seed(1)
+    m = scHPF(5, verbose=False)
+    m._initialize(X)
+    assert m.bp == float(g["bp"]) and m.dp == float(g["dp"])       # reference asserts equality too
+    for name in ("theta", "beta", "xi", "eta"):
+        assert_equal(getattr(m, name).vi_shape, g["init_%s_shp" % name])
+        assert_equal(getattr(m, name).vi_rate, g["init_%s_rte" % name])
+    assert m.ncells == 1000 and m.ngenes == 2000
+
+
+def test_hyperparameter_rules():
+    m = scHPF(9, a=-2, c=-2)
+    assert m.a == 1 / 3 and m.c == 1 / 3                            # -2 -> 1/sqrt(K)
+    with pytest.raises(ValueError):
+        scHPF(None, a=-2)
+    with pytest.raises(ValueError):
+        scHPF(3).project(None, replace=True, recalc_bp=True)
+    X = coo_matrix((np.ones(3, dtype=np.int32), (np.arange(3), np.arange(3))), shape=(3, 3))
+    with pytest.raises(ValueError):
+        scHPF(2, bp=1.0)._setup(X, freeze_genes=True)                # frozen genes without dp
+    with pytest.raises(ValueError):
+        scHPF(2, bp=1.0, dp=1.0)._setup(X, freeze_genes=True)        # ... without eta / beta
+
+
+@pytest.mark.parametrize("n", [1, 10, 50])
+def test_fit_loop_reproduces_reference(oracle_backend, g_cavi, n):
+    g, X = g_cavi, _X(g_cavi)
+    m = scHPF(5, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]),
+              xi=_gam(g, "xi", "init_"), theta=_gam(g, "theta", "init_"),
+              eta=_gam(g, "eta", "init_"), beta=_gam(g, "beta", "init_"))
+    m.fit(X, reinit=False, min_iter=n, max_iter=n, check_freq=int(g["it%d_check_freq" % n]))
+    for name in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(m, name).vi_shape, g["it%d_%s_shp" % (n, name)]) < 1e-10
+        assert max_rel(getattr(m, name).vi_rate, g["it%d_%s_rte" % (n, name)]) < 1e-10
+    assert_allclose(m.loss, g["it%d_loss" % n], rtol=1e-12)
+
+
+def test_fit_with_reinit_reproduces_seeded_reference(oracle_backend, g_reinit):
+    g, X = g_reinit, _X(g_reinit)
+    np.random.seed(int(g["seed"]))
+    m = scHPF(3, verbose=False).fit(X, min_iter=6, max_iter=6, check_freq=2)
+    assert m.bp == float(g["bp"]) and m.dp == float(g["dp"])
+    for name in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(m, name).vi_shape, g[name + "_shp"]) < 1e-11
+        assert max_rel(getattr(m, name).vi_rate, g[name + "_rte"]) < 1e-11
+    assert_allclose(m.loss, g["loss"], rtol=1e-12)
+
+
+def test_simultaneous_updates(oracle_backend, g_simul):
+    g, X = g_simul, _X(g_simul)
+    m = scHPF(3, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]),
+              xi=_gam(g, "xi", "init_"), theta=_gam(g, "theta", "init_"),
+              eta=_gam(g, "eta", "init_"), beta=_gam(g, "beta", "init_"))
+    m.fit(X, reinit=False, min_iter=7, max_iter=7, check_freq=2, beta_theta_simultaneous=True)
+    for name in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(m, name).vi_shape, g["fin_%s_shp" % name]) < 1e-11
+    assert_allclose(m.loss, g["loss"], rtol=1e-12)
+
+
+def test_project_reproduces_reference(oracle_backend, g_cavi, g_project):
+    g, p = g_cavi, g_project
+    trained = scHPF(5, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]),
+                    xi=_gam(g, "xi", "it50_"), theta=_gam(g, "theta", "it50_"),
+                    eta=_gam(g, "eta", "it50_"), beta=_gam(g, "beta", "it50_"))
+    Xn = _X(p)
+    np.random.seed(int(p["seed"]))
+    proj = trained.project(Xn, min_iter=10, max_iter=10, check_freq=2)
+    assert proj is not trained and proj.ncells == 200
+    assert proj.eta == trained.eta and proj.beta == trained.beta     # bit-exact, as the reference tests
+    assert proj.bp == trained.bp == float(p["bp"])
+    assert max_rel(proj.theta.vi_shape, p["theta_shp"]) < 1e-11
+    assert max_rel(proj.theta.vi_rate, p["theta_rte"]) < 1e-11
+    assert max_rel(proj.xi.vi_rate, p["xi_rte"]) < 1e-11
+    assert_allclose(proj.loss, p["loss"], rtol=1e-12)
+    assert_allclose(proj.cell_score(), p["cell_score"], rtol=1e-10)
+    # transform == cell scores of a fresh projection
+    np.random.seed(int(p["seed"]))
+    assert_allclose(trained.transform(Xn, min_iter=10, max_iter=10, check_freq=2), p["cell_score"], rtol=1e-10)
+    # replace=True writes xi/theta into the model and returns the loss list
+    np.random.seed(int(p["seed"]))
+    loss = trained.project(Xn, replace=True, min_iter=10, max_iter=10, check_freq=2)
+    assert_allclose(loss, p["loss"], rtol=1e-12)
+    assert trained.ncells == 200
+    # recalc_bp recomputes b' from the new data
+    recalc = trained.project(Xn, recalc_bp=True, min_iter=2, max_iter=2)
+    rs = np.asarray(Xn.sum(axis=1))
+    assert recalc.bp == trained.ap * np.mean(rs) / np.var(rs)
+
+
+def test_scores_against_reference(g_kernels):
+    g = g_kernels
+    m = scHPF(4, xi=_gam(g, "xi"), theta=_gam(g, "theta"), eta=_gam(g, "eta"), beta=_gam(g, "beta"))
+    assert_equal(m.cell_score(), g["cell_score"])
+    assert_equal(m.gene_score(), g["gene_score"])
+
+
+def test_convergence_rules(oracle_backend, g_cavi):
+    """Scripted losses drive the stopping rules of scHPF_.py:750-774.  The expected
+    lengths were produced by the reference itself on the same scripts."""
+    g, X = g_cavi, _X(g_cavi)
+
+    def run(seq, **kw):
+        it = iter(seq)
+        m = scHPF(5, verbose=False, epsilon=0.001, better_than_n_ago=5)
+        m.fit(X, loss_function=lambda **k: next(it), min_iter=0, max_iter=200, check_freq=1, **kw)
+        return m.loss
+    # converges at the 2nd consecutive small change once more than 3 checks exist
+    flat = [10, 9, 8, 7.99999, 7.999985, 7.99998, 1, 1, 1]
+    assert len(run(flat)) == 5
+    # an inflection (prev is a local max) blocks convergence for that check
+    infl = [10.0, 8.0, 8.00001, 8.000005, 8.0000049, 3, 3, 3, 3]
+    assert len(run(infl)) == 5
+    # getting worse than better_than_n_ago checks ago, and rising -> stop
+    worse = [5, 4, 3, 2, 1, 1.5, 2.5, 9, 9, 9]
+    assert len(run(worse)) == 8
+    # loss_smoothing averages the last n raw values
+    m_loss = run([4.0, 2.0, 6.0, 8.0] + [8.0] * 200, loss_smoothing=2)
+    assert m_loss[:4] == [4.0, 3.0, 4.0, 7.0]
+    # check schedule: losses at t = 0, cf, 2cf, ... ; max_iter=10, check_freq=10 -> one entry
+    m = scHPF(5, verbose=False).fit(X, max_iter=10, min_iter=10, check_freq=10)
+    assert len(m.loss) == 1
+    m = scHPF(5, verbose=False).fit(X, max_iter=11, min_iter=11, check_freq=5)
+    assert len(m.loss) == 3
+
+
+def test_checkstep_function_and_custom_loss_get_host_state(oracle_backend, g_cavi):
+    X = _X(g_cavi)
+    seen = []
+
+    def checkstep(bp, dp, xi, eta, theta, beta, t):
+        assert isinstance(theta, HPF_Gamma) and theta.dims == (1000, 5) and beta.dims == (2000, 5)
+        seen.append(t)
+    np.random.seed(0)
+    m = scHPF(5, verbose=False).fit(X, max_iter=7, min_iter=7, check_freq=3, checkstep_function=checkstep)
+    assert seen == [0, 3, 6] and len(m.loss) == 3
+    with pytest.raises(NotImplementedError):
+        scHPF(5, verbose=False).fit(X, batchsize=100, max_iter=2)
+
+
+def test_combine_across_cells(g_kernels):
+    g = g_kernels
+    x = scHPF(4, bp=1.0, dp=2.0, xi=_gam(g, "xi"), theta=_gam(g, "theta"), eta=_gam(g, "eta"), beta=_gam(g, "beta"))
+    y = scHPF(4, bp=3.0, dp=2.0, xi=HPF_Gamma(g["xi_shp"][:5] + 1, g["xi_rte"][:5] + 1),
+              theta=HPF_Gamma(g["theta_shp"][:5] + 1, g["theta_rte"][:5] + 1), eta=x.eta, beta=x.beta)
+    ixs = np.array([0, 2, 4, 6, 304])
+    xy = combine_across_cells(x, y, ixs)
+    assert xy.bp is None and xy.ncells == 305
+    assert_equal(xy.theta.vi_shape[ixs], y.theta.vi_shape)
+    assert_equal(xy.theta.vi_shape[np.setdiff1d(np.arange(305), ixs)], x.theta.vi_shape)
+
+
+def test_model_roundtrips_through_joblib(tmp_path, g_kernels):
+    g = g_kernels
+    m = scHPF(4, bp=1.0, dp=2.0, xi=_gam(g, "xi"), theta=_gam(g, "theta"), eta=_gam(g, "eta"), beta=_gam(g, "beta"))
+    f = str(tmp_path / "m.joblib")
+    schpf_b200.save_model(m, f)
+    m2 = schpf_b200.load_model(f)
+    assert m2.theta == m.theta and m2.beta == m.beta and m2.a == m.a
+
+
+# --------------------------------------------------------------- sharding ----
+def test_shard_bounds_balance_nnz():
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 500, size=10007)
+    for ws in (1, 2, 3, 8):
+        b = shard_bounds_by_nnz(counts, ws)
+        assert b[0] == 0 and b[-1] == counts.shape[0] and np.all(np.diff(b) >= 0) and len(b) == ws + 1
+        per = np.array([counts[b[r]:b[r + 1]].sum() for r in range(ws)])
+        assert per.sum() == counts.sum()
+        assert per.max() - per.min() <= 2 * counts.max()
+    # degenerate: all nonzeros in one cell, empty matrix
+    assert list(shard_bounds_by_nnz([0, 0, 9, 0], 2)) in ([0, 2, 4], [0, 3, 4])
+    assert list(shard_bounds_by_nnz([0, 0, 0], 2))[0] == 0
