@@ -99,7 +99,8 @@ def test_kernels_against_oracle_random(K):
     ts, tr = rng.gamma(2.0, 1.0, (C, K)) + 1e-3, rng.gamma(2.0, 1.0, (C, K)) + 1e-3
     bs, br = rng.gamma(0.5, 1.0, (G, K)) + 1e-3, rng.gamma(2.0, 1.0, (G, K)) + 1e-3
     xphi = hpf_cuda.compute_Xphi_data(data, row, col, ts, tr, bs, br)
-    assert_allclose(xphi, oc.compute_Xphi_data(data, row, col, ts, tr, bs, br), rtol=1e-11, atol=0)
+    # atol: entries that underflow to subnormals differ in their last bits
+    assert_allclose(xphi, oc.compute_Xphi_data(data, row, col, ts, tr, bs, br), rtol=1e-11, atol=1e-300)
     assert_allclose(hpf_cuda.compute_loading_shape_update(xphi, col, G, 0.3),
                     oc.compute_loading_shape_update(xphi, col, G, 0.3), rtol=1e-13)
     assert_allclose(hpf_cuda.compute_pois_llh(data, row, col, ts, tr, bs, br),
