@@ -132,6 +132,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     } while (!done);
 }
 
+// 128-bit shared-memory load from a 32-bit shared address (no generic-address arithmetic)
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
 // streaming 128-bit load that does not allocate in L1 (entry stream is read once)
 __device__ __forceinline__ int4 ld_stream_int4(const int4 *p)
 {

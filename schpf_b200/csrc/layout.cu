@@ -10,12 +10,18 @@
 //   slots = one warp (one owner per lane pair), `warps` warps = one CTA block;
 //   the other axis is cut into panels of `panel_rows` rows;
 //   for every (warp, panel) the 16 owners' nonzeros inside that panel are
-//   stored step-interleaved (step i of all 16 pairs is contiguous), padded to
-//   the longest of the 16 lists rounded up to an even number of steps, two
-//   steps per int4 {other_local | pad<<31, y, other_local | pad<<31, y};
-//   within a list, nonzeros are ordered by ((other_local - slot) mod 4, other_local)
-//   so that the four lane pairs of a quarter warp tend to read shared-memory rows
-//   of four different bank groups in the same step.
+//   stored step-interleaved (step i of all 16 pairs is contiguous), two steps
+//   per int4 {other_local | pad<<31, y, other_local | pad<<31, y};
+//   WHICH nonzero a pair handles at which step is a conflict-free schedule: a
+//   shared-memory row of the panel falls into bank group (other_local mod 4),
+//   and the four lane pairs of a quarter warp are served by one wavefront only
+//   if they read four different groups.  For each (quarter warp, panel) the
+//   4 owners x 4 groups count matrix is a bipartite multigraph; it is edge-
+//   coloured with Delta = max(row sums, column sums) colours (Koenig), one
+//   colour = one step = a partial permutation owners -> groups.  Pairs with no
+//   edge of a colour get a pad entry (their loads are predicated off).  The
+//   (warp, panel) block has max over its 4 quarter warps of Delta steps,
+//   rounded up to even.
 //
 // Integer work only; results are bit-exact and independent of the input order
 // of the triples (ties are broken by the other-axis index, duplicates by the
@@ -72,15 +78,36 @@ __global__ void make_keys_kernel(int64_t nnz, const int32_t *__restrict__ own, c
     const int32_t p = t / panel_rows;
     const int32_t tl = t - p * panel_rows;
     const int64_t seg = (int64_t)slot * npanel + p;
-    const uint32_t rot = (uint32_t)(tl - slot) & 3u;
-    keys[i] = ((uint64_t)seg << (KEY_LOCAL_BITS + KEY_ROT_BITS)) | ((uint64_t)rot << KEY_LOCAL_BITS) |
+    const uint32_t cls = (uint32_t)tl & 3u;
+    keys[i] = ((uint64_t)seg << (KEY_LOCAL_BITS + KEY_ROT_BITS)) | ((uint64_t)cls << KEY_LOCAL_BITS) |
               (uint64_t)tl;
     vals[i] = ((uint64_t)(uint32_t)val[i] << 32) | (uint64_t)(uint32_t)tl;
-    atomicAdd(reinterpret_cast<unsigned long long *>(seg_cnt + seg), 1ULL);
+    atomicAdd(reinterpret_cast<unsigned long long *>(seg_cnt + seg * 4 + cls), 1ULL);
 }
 
-// step pairs per (warp, panel) = ceil(max over the warp's 16 lists / 2)
-__global__ void warp_steps_kernel(int64_t n_warps, int npanel, const int64_t *__restrict__ seg_cnt,
+// ---- conflict-free schedule of one (quarter warp, panel) ----------------------
+// n[o][c]: nonzeros of owner o (0..3, one per lane pair) whose panel-local row is in
+// bank group c.  Delta = max(row sums, column sums) steps suffice and are necessary.
+__device__ __forceinline__ int qw_delta(const int64_t *__restrict__ cnt4 /* 4 owners x [npanel*4] */,
+                                        int64_t base0, int64_t owner_stride, int n[4][4])
+{
+    int rs[4] = {0, 0, 0, 0}, cs[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            n[o][c] = (int)cnt4[base0 + o * owner_stride + c];
+            rs[o] += n[o][c];
+            cs[c] += n[o][c];
+        }
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d = max(d, max(rs[i], cs[i]));
+    return d;
+}
+
+// step pairs per (warp, panel) = ceil(max over the warp's 4 quarter warps of Delta / 2)
+__global__ void warp_steps_kernel(int64_t n_warps, int npanel, const int64_t *__restrict__ cnt4,
                                   int64_t *__restrict__ pairs)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,10 +118,11 @@ __global__ void warp_steps_kernel(int64_t n_warps, int npanel, const int64_t *__
         pairs[idx] = 0;
         return;
     }
-    int64_t m = 0;
-    for (int q = 0; q < GROUPS_PER_WARP; ++q) {
-        const int64_t c = seg_cnt[(wg * GROUPS_PER_WARP + q) * npanel + p];
-        m = c > m ? c : m;
+    int m = 0;
+    for (int qw = 0; qw < 4; ++qw) {
+        int n[4][4];
+        const int64_t slot0 = wg * GROUPS_PER_WARP + qw * 4;
+        m = max(m, qw_delta(cnt4, (slot0 * npanel + p) * 4, (int64_t)npanel * 4, n));
     }
     pairs[idx] = (m + 1) >> 1;
 }
@@ -105,21 +133,80 @@ __global__ void fill_pad_kernel(int64_t n_int4, int4 *entries)
     if (i < n_int4) entries[i] = make_int4((int)0x80000000, 0, (int)0x80000000, 0);
 }
 
-__global__ void place_entries_kernel(int64_t nnz, const uint64_t *__restrict__ keys,
-                                     const uint64_t *__restrict__ vals, const int64_t *__restrict__ seg_first,
-                                     const int64_t *__restrict__ seg_ptr, int npanel, int2 *__restrict__ entries)
+// the 24 permutations of {0,1,2,3}, 2 bits per element
+__constant__ unsigned char PERM4[24] = {
+    0xE4, 0xB4, 0xD8, 0x78, 0x9C, 0x6C, 0xE1, 0xB1, 0xC9, 0x39, 0x8D, 0x2D,
+    0xD2, 0x72, 0xC6, 0x36, 0x4E, 0x1E, 0x93, 0x63, 0x87, 0x27, 0x4B, 0x1B};
+
+// One thread per (quarter warp, panel): colour the 4x4 multigraph and copy each nonzero
+// to its (step, pair) slot.  At a step with R steps left, every row / column whose
+// remaining degree equals R must be matched (then the maximum degree drops to R-1); a
+// matching doing so always exists in a bipartite multigraph, and with 4+4 vertices the
+// 24 permutations are simply tried.
+__global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__restrict__ cnt4,
+                                     const int64_t *__restrict__ first4, const uint64_t *__restrict__ vals,
+                                     const int64_t *__restrict__ seg_ptr, int2 *__restrict__ entries,
+                                     int *__restrict__ unplaced)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nnz) return;
-    const int64_t seg = (int64_t)(keys[j] >> (KEY_LOCAL_BITS + KEY_ROT_BITS));
-    const int64_t slot = seg / npanel;
-    const int p = (int)(seg - slot * npanel);
-    const int64_t rank = j - seg_first[seg];
-    const int64_t wg = slot / GROUPS_PER_WARP;
-    const int q = (int)(slot - wg * GROUPS_PER_WARP);
-    const int64_t pair = seg_ptr[wg * (npanel + 1) + p] + (rank >> 1);
-    const uint64_t v = vals[j];
-    entries[(pair * GROUPS_PER_WARP + q) * 2 + (rank & 1)] = make_int2((int)(uint32_t)v, (int)(uint32_t)(v >> 32));
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_qw * npanel) return;
+    const int64_t qwg = idx / npanel;              // global quarter-warp index
+    const int p = (int)(idx - qwg * npanel);
+    const int64_t slot0 = qwg * 4;
+    const int64_t wg = slot0 / GROUPS_PER_WARP;
+    const int q0 = (int)(slot0 - wg * GROUPS_PER_WARP);
+    const int64_t base0 = (slot0 * npanel + p) * 4, ostride = (int64_t)npanel * 4;
+    int n[4][4], used[4][4];
+    const int delta = qw_delta(cnt4, base0, ostride, n);
+    if (delta == 0) return;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) used[o][c] = 0;
+    int rs[4], cs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rs[i] = n[i][0] + n[i][1] + n[i][2] + n[i][3];
+        cs[i] = n[0][i] + n[1][i] + n[2][i] + n[3][i];
+    }
+    const int64_t pair0 = seg_ptr[wg * (npanel + 1) + p];
+    for (int step = 0; step < delta; ++step) {
+        const int R = delta - step;
+        int best = -1, best_score = -1;
+        for (int k = 0; k < 24; ++k) {
+            const unsigned pm = PERM4[k];
+            bool ok = true;
+            int score = 0;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int c = (pm >> (2 * o)) & 3;
+                const bool has = n[o][c] > 0;
+                score += has;
+                if (!has && (rs[o] == R || cs[c] == R)) ok = false;
+            }
+            if (ok && score > best_score) {
+                best = k;
+                best_score = score;
+            }
+        }
+        if (best < 0) best = 0;   // cannot happen (Koenig); keeps the loop well defined
+        const unsigned pm = PERM4[best];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int c = (pm >> (2 * o)) & 3;
+            if (n[o][c] > 0) {
+                const int64_t src = first4[base0 + o * ostride + c] + used[o][c];
+                const uint64_t v = vals[src];
+                const int64_t dst = ((pair0 + (step >> 1)) * GROUPS_PER_WARP + (q0 + o)) * 2 + (step & 1);
+                entries[dst] = make_int2((int)(uint32_t)v, (int)(uint32_t)(v >> 32));
+                ++used[o][c];
+                --n[o][c];
+                --rs[o];
+                --cs[c];
+            }
+        }
+    }
+    if (rs[0] | rs[1] | rs[2] | rs[3]) atomicAdd(unplaced, 1);   // schedule incomplete: never expected
 }
 
 struct DevBuf {
@@ -175,13 +262,15 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
 
     const int64_t n_slots = (int64_t)L.nblocks * owners_per_block;
     const int64_t n_warps = (int64_t)L.nblocks * warps;
-    const int64_t n_seg = n_slots * L.npanel;
+    const int64_t n_seg = n_slots * L.npanel * 4;   // (slot, panel, bank group) lists
     const int64_t n_ptr = n_warps * (L.npanel + 1);
 
     CUDA_TRY(cudaMalloc(&L.own_id, sizeof(int32_t) * n_slots));
     CUDA_TRY(cudaMalloc(&L.seg_ptr, sizeof(int64_t) * n_ptr));
 
-    DevBuf cnt, ids, cnt_sorted, ids_sorted, slot_of, seg_cnt, seg_first, pairs, keys, vals, keys2, vals2, tmp;
+    DevBuf cnt, ids, cnt_sorted, ids_sorted, slot_of, seg_cnt, seg_first, pairs, keys, vals, keys2, vals2, tmp, unplaced;
+    CUDA_TRY(unplaced.alloc(sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(unplaced.p, 0, sizeof(int), stream));
     CUDA_TRY(cnt.alloc(sizeof(int32_t) * n_own));
     CUDA_TRY(ids.alloc(sizeof(int32_t) * n_own));
     CUDA_TRY(cnt_sorted.alloc(sizeof(int32_t) * n_own));
@@ -204,7 +293,7 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
                                                        ids.as<int32_t>(), ids_sorted.as<int32_t>(), (int)n_own,
                                                        0, 32, stream));
     tmp_bytes = need;
-    const int key_bits = KEY_LOCAL_BITS + KEY_ROT_BITS + bits_for((uint64_t)(n_seg > 0 ? n_seg - 1 : 0));
+    const int key_bits = KEY_LOCAL_BITS + KEY_ROT_BITS + bits_for((uint64_t)(n_seg > 4 ? n_seg / 4 - 1 : 0));
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, keys.as<uint64_t>(), keys2.as<uint64_t>(),
                                              vals.as<uint64_t>(), vals2.as<uint64_t>(), nnz, 0, key_bits, stream));
     if (need > tmp_bytes) tmp_bytes = need;
@@ -249,12 +338,21 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     const int64_t n_int4 = total_pairs * GROUPS_PER_WARP;
     CUDA_TRY(cudaMalloc(&L.entries, sizeof(int4) * (n_int4 > 0 ? n_int4 : 1)));
     if (n_int4 > 0) fill_pad_kernel<<<blocks_for(n_int4, 256), 256, 0, stream>>>(n_int4, L.entries);
-    if (nnz > 0)
-        place_entries_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(
-            nnz, keys2.as<uint64_t>(), vals2.as<uint64_t>(), seg_first.as<int64_t>(), L.seg_ptr, L.npanel,
-            reinterpret_cast<int2 *>(L.entries));
+    if (nnz > 0) {
+        const int64_t n_qw = n_slots / 4;
+        place_entries_kernel<<<blocks_for(n_qw * L.npanel, 128), 128, 0, stream>>>(
+            n_qw, L.npanel, seg_cnt.as<int64_t>(), seg_first.as<int64_t>(), vals2.as<uint64_t>(), L.seg_ptr,
+            reinterpret_cast<int2 *>(L.entries), unplaced.as<int>());
+    }
     CUDA_TRY(cudaGetLastError());
+    int n_unplaced = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_unplaced, unplaced.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));   // temporaries are freed on return
+    if (n_unplaced) {
+        set_error("layout: %d (quarter warp, panel) schedules left nonzeros unplaced", n_unplaced);
+        L.release();
+        return SCHPF_ERR_STATE;
+    }
     L.bytes = sizeof(int32_t) * n_slots + sizeof(int64_t) * n_ptr + sizeof(int4) * n_int4;
     return SCHPF_OK;
 }

@@ -40,7 +40,7 @@ __host__ __device__ constexpr int sweep_max_warps(int KP)
 {
     // registers are granted per SM sub-partition (16384 each): what counts is warps per
     // sub-partition, so CTA sizes are multiples of 4 warps where the budget is tight
-    return KP <= 16 ? 10 : KP <= 28 ? 8 : KP <= 32 ? 6 : KP <= 40 ? 12 : 8;
+    return KP <= 12 ? 10 : KP <= 20 ? 8 : KP <= 32 ? 6 : 8;
 }
 
 template <int KP>
@@ -91,6 +91,7 @@ sweep_kernel(const SweepArgs A)
     __syncthreads();
 
     uint32_t parity = 0;
+    const uint32_t panel_s = smem_u32(panel);
     const int64_t *sp = A.seg_ptr + (int64_t)wg * (A.npanel + 1);
 
     for (int p = p0; p < p1; ++p) {
@@ -110,35 +111,55 @@ sweep_kernel(const SweepArgs A)
             ep += GROUPS_PER_WARP;
             int4 nxt = cur;
             if (i + 1 < i1) nxt = ld_stream_int4(ep);
+            // two steps per iteration, written as one straight-line block so that the two
+            // independent dot products / divisions interleave
+            const int ex[2] = {cur.x, cur.z}, ey[2] = {cur.y, cur.w};
+            double bv[2][D], s[2];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int ex = half ? cur.z : cur.x;
-                const int ey = half ? cur.w : cur.y;
-                const int t = ex & 0x7fffffff;
-                const double2 *rp = reinterpret_cast<const double2 *>(panel) + (t * (ST / 2) + h);
-                double bv[D];
+            for (int e = 0; e < 2; ++e) {
+                // pad entries (bit 31) read nothing: no wavefront, no bank conflict
+                const uint32_t addr = panel_s + (uint32_t)(ex[e] & 0x7fffffff) * (ST * 8) + h * 16;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
-                    const double2 v = rp[2 * j];
-                    bv[2 * j] = v.x;
-                    bv[2 * j + 1] = v.y;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (ex[e] >= 0) v = lds_f64x2(addr + j * 32);
+                    bv[e][2 * j] = v.x;
+                    bv[e][2 * j + 1] = v.y;
                 }
-                double s = a[0] * bv[0];
+            }
 #pragma unroll
-                for (int k = 1; k < D; ++k) s = fma(a[k], bv[k], s);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                const double y = (double)ey;
-                if (MODE == SWEEP_SHAPE) {
-                    const bool ok = s > TINY_NORMALIZER;
-                    const double w = ok ? div_pos(y, s) : 0.0;
+            for (int e = 0; e < 2; ++e) {
+                double s0 = a[0] * bv[e][0], s1 = a[1] * bv[e][1];
 #pragma unroll
-                    for (int k = 0; k < D; ++k) acc[k] = fma(w, bv[k], acc[k]);
-                    if (!ok && ey != 0 && own >= 0) {
-                        // log-space redo of this nonzero (hpf_numba.py:98-112); both lanes of the pair
-                        // get here together.  Rare: kept rolled so it costs the hot path no registers.
-                        const int K = A.K;
+                for (int k = 2; k < D; k += 2) {
+                    s0 = fma(a[k], bv[e][k], s0);
+                    s1 = fma(a[k + 1], bv[e][k + 1], s1);
+                }
+                s[e] = s0 + s1;
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 1);
+            if (MODE == SWEEP_SHAPE) {
+                bool slow = false;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double y = (double)ey[e];
+                    const bool ok = s[e] > TINY_NORMALIZER;
+                    const double w = ok ? div_pos(y, s[e]) : 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) acc[k] = fma(w, bv[e][k], acc[k]);
+                    slow |= (!ok && ey[e] != 0);
+                }
+                if (slow && own >= 0) {
+                    // log-space redo of an underflowed nonzero (hpf_numba.py:98-112); both lanes of
+                    // the pair get here together.  Rare: kept rolled, costs the hot path no registers.
+                    const int K = A.K;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (s[e] > TINY_NORMALIZER || ey[e] == 0) continue;
+                        const double y = (double)ey[e];
                         const double *eo = A.own_elog + (int64_t)own * K;
-                        const double *et = A.oth_elog + ((int64_t)p * A.panel_rows + t) * K;
+                        const double *et = A.oth_elog + ((int64_t)p * A.panel_rows + (ex[e] & 0x7fffffff)) * K;
                         double largest = -INFINITY, normalizer = 0.0;
 #pragma unroll 1
                         for (int k = 0; k < K; ++k) largest = fmax(largest, eo[k] + et[k]);
@@ -146,17 +167,21 @@ sweep_kernel(const SweepArgs A)
                         for (int k = 0; k < K; ++k) normalizer += exp(eo[k] + et[k] - largest);
 #pragma unroll 1
                         for (int k = 2 * h; k < K; k += 4) {
-                            atomicAdd(A.direct + (int64_t)own * K + k, y * exp(eo[k] + et[k] - largest) / normalizer);
+                            atomicAdd(A.direct + (int64_t)own * K + k,
+                                      y * exp(eo[k] + et[k] - largest) / normalizer);
                             if (k + 1 < K)
                                 atomicAdd(A.direct + (int64_t)own * K + k + 1,
                                           y * exp(eo[k + 1] + et[k + 1] - largest) / normalizer);
                         }
                         if (h == 0) atomicAdd(A.slow_hits, 1ULL);
                     }
-                } else {
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
                     // hpf_numba.py:49-50 without the lgamma term (a constant of the data)
-                    const double v = fma(y, log(s), -s);
-                    if (ex >= 0 && h == 0) llh += v;
+                    const double v = fma((double)ey[e], log(s[e]), -s[e]);
+                    if (ex[e] >= 0 && h == 0) llh += v;
                 }
             }
             cur = nxt;
