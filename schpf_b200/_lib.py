@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libschpf_b200.so")
+LIB_PATH = os.environ.get("SCHPF_B200_LIB") or os.path.join(_HERE, "_C", "libschpf_b200.so")
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

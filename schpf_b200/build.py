@@ -10,14 +10,17 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(HERE, "csrc")
-OUT_DIR = os.path.join(HERE, "_C")
+# experiments: SCHPF_BUILD_TAG=<name> SCHPF_NVCC_FLAGS="-DSWEEP_INTERLEAVE=0 ..." builds
+# _C_<name>/libschpf_b200.so, which SCHPF_B200_LIB can then point the loader at
+_TAG = os.environ.get("SCHPF_BUILD_TAG", "")
+OUT_DIR = os.path.join(HERE, "_C" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(OUT_DIR, "libschpf_b200.so")
 SOURCES = ["engine.cu", "sweep.cu", "layout.cu", "dense.cu", "shims.cu"]
 HEADERS = [os.path.join(SRC_DIR, "common.cuh"),
            os.path.join(HERE, "..", "include", "schpf_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("SCHPF_NVCC_FLAGS", "").split()
 
 
 def _newer(a, b):

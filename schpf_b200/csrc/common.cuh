@@ -76,19 +76,16 @@ __device__ __forceinline__ double digamma_pos(double x)
     return log(s) - 0.5 / s - y - w;
 }
 
-// y / s for a normal positive s: hardware seed (MUFU.RCP64H, ~20 bits), two
-// Newton steps, then one residual correction of the quotient (error < 1 ulp).
+// y / s for a normal positive s: hardware seed (MUFU.RCP64H, relative error e ~ 2^-20),
+// one cubic Newton step r(1 + e + e^2) (error e^3 ~ 2^-60), then the product: < 2 ulp.
 __device__ __forceinline__ double div_pos(double y, double s)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
-    double e = fma(-s, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-s, r, 1.0);
-    r = fma(r, e, r);
-    double q = y * r;
-    const double rem = fma(-s, q, y);
-    return fma(rem, r, q);
+    const double e = fma(-s, r, 1.0);
+    const double t = fma(e, e, e);
+    r = fma(r, t, r);
+    return y * r;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -138,6 +135,18 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
+}
+
+// The same, predicated on `word >= 0` (pad entries have bit 31 set): a pad issues no
+// load at all -- no wavefront, no bank conflict -- and leaves x, y as they were.
+__device__ __forceinline__ void lds_f64x2_unless_pad(double &x, double &y, uint32_t addr, int word)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ge.s32 p, %3, 0;\n\t"
+        "@p ld.shared.v2.f64 {%0, %1}, [%2];\n\t}"
+        : "+d"(x), "+d"(y)
+        : "r"(addr), "r"(word));
 }
 
 // streaming 128-bit load that does not allocate in L1 (entry stream is read once)

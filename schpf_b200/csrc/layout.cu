@@ -19,7 +19,8 @@
 //   4 owners x 4 groups count matrix is a bipartite multigraph; it is edge-
 //   coloured with Delta = max(row sums, column sums) colours (Koenig), one
 //   colour = one step = a partial permutation owners -> groups.  Pairs with no
-//   edge of a colour get a pad entry (their loads are predicated off).  The
+//   edge of a colour get a pad entry (count 0) pointing at a row of the group
+//   the permutation leaves them, so pads never conflict either.  The
 //   (warp, panel) block has max over its 4 quarter warps of Delta steps,
 //   rounded up to even.
 //
@@ -130,7 +131,10 @@ __global__ void warp_steps_kernel(int64_t n_warps, int npanel, const int64_t *__
 __global__ void fill_pad_kernel(int64_t n_int4, int4 *entries)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_int4) entries[i] = make_int4((int)0x80000000, 0, (int)0x80000000, 0);
+    // pads read a real row of the bank group their lane pair would own in an all-pad step
+    // (rows 0..3 are in groups 0..3), so they never conflict with each other
+    const int o = (int)(i % GROUPS_PER_WARP) & 3;
+    if (i < n_int4) entries[i] = make_int4((int)0x80000000 | o, 0, (int)0x80000000 | o, 0);
 }
 
 // the 24 permutations of {0,1,2,3}, 2 bits per element
@@ -194,15 +198,18 @@ __global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
             const int c = (pm >> (2 * o)) & 3;
+            const int64_t dst = ((pair0 + (step >> 1)) * GROUPS_PER_WARP + (q0 + o)) * 2 + (step & 1);
             if (n[o][c] > 0) {
                 const int64_t src = first4[base0 + o * ostride + c] + used[o][c];
                 const uint64_t v = vals[src];
-                const int64_t dst = ((pair0 + (step >> 1)) * GROUPS_PER_WARP + (q0 + o)) * 2 + (step & 1);
                 entries[dst] = make_int2((int)(uint32_t)v, (int)(uint32_t)(v >> 32));
                 ++used[o][c];
                 --n[o][c];
                 --rs[o];
                 --cs[c];
+            } else {
+                // idle pair: a pad that reads row c, the bank group this permutation leaves it
+                entries[dst] = make_int2((int)(0x80000000u | (unsigned)c), 0);
             }
         }
     }

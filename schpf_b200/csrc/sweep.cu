@@ -32,6 +32,17 @@ namespace {
 
 constexpr int SWEEP_MAX_WARPS = 12;
 
+// build-time experiment knobs (python -m schpf_b200.build reads SCHPF_NVCC_FLAGS)
+#ifndef SWEEP_INTERLEAVE
+#define SWEEP_INTERLEAVE 1
+#endif
+#ifndef SWEEP_W20
+#define SWEEP_W20 8
+#endif
+#ifndef SWEEP_PAD_PRED
+#define SWEEP_PAD_PRED 0
+#endif
+
 // A lane keeps 3*KP/2 doubles live (owner row, accumulators, streamed row) plus
 // ~44 registers of addressing: the CTA shape is picked per KP so that this fits
 // the register file without spilling (ptxas -v is checked in DESIGN.md §4).
@@ -40,7 +51,7 @@ __host__ __device__ constexpr int sweep_max_warps(int KP)
 {
     // registers are granted per SM sub-partition (16384 each): what counts is warps per
     // sub-partition, so CTA sizes are multiples of 4 warps where the budget is tight
-    return KP <= 12 ? 10 : KP <= 20 ? 8 : KP <= 32 ? 6 : 8;
+    return KP <= 12 ? 10 : KP <= 16 ? 8 : KP <= 20 ? SWEEP_W20 : KP <= 32 ? 6 : 8;
 }
 
 template <int KP>
@@ -83,6 +94,13 @@ sweep_kernel(const SweepArgs A)
         acc[2 * j + 1] = 0.0;
     }
     double llh = 0.0;
+#if SWEEP_PAD_PRED
+    // streamed rows of the step(s) in flight; they persist across iterations so that pad
+    // entries can skip their loads and reuse the previous (finite) values with weight 0
+    double bv[SWEEP_INTERLEAVE ? 2 : 1][D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) bv[0][k] = bv[SWEEP_INTERLEAVE ? 1 : 0][k] = 0.0;
+#endif
 
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -102,29 +120,39 @@ sweep_kernel(const SweepArgs A)
         }
         const int64_t i0 = sp[p], i1 = sp[p + 1];
         const int4 *ep = A.entries + i0 * GROUPS_PER_WARP + q;
-        int4 cur = make_int4(0, 0, 0, 0);
+        // the entry stream comes straight from HBM: keep two iterations in flight per lane
+        int4 cur = make_int4(0, 0, 0, 0), nxt = cur;
         if (i0 < i1) cur = ld_stream_int4(ep);
+        if (i0 + 1 < i1) nxt = ld_stream_int4(ep + GROUPS_PER_WARP);
         mbar_wait(mbar, parity);
         parity ^= 1u;
 
         for (int64_t i = i0; i < i1; ++i) {
             ep += GROUPS_PER_WARP;
-            int4 nxt = cur;
-            if (i + 1 < i1) nxt = ld_stream_int4(ep);
-            // two steps per iteration, written as one straight-line block so that the two
-            // independent dot products / divisions interleave
+            int4 nxt2 = nxt;
+            if (i + 2 < i1) nxt2 = ld_stream_int4(ep + GROUPS_PER_WARP);
             const int ex[2] = {cur.x, cur.z}, ey[2] = {cur.y, cur.w};
-            double bv[2][D], s[2];
+            double s[2];
+            bool slow = false;
+#if SWEEP_INTERLEAVE
+            // two steps per iteration as one straight-line block: the two independent dot
+            // products / divisions interleave (more ILP, 2*D more live registers)
+#if !SWEEP_PAD_PRED
+            double bv[2][D];
+#endif
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                // pad entries (bit 31) read nothing: no wavefront, no bank conflict
+                // pad entries (bit 31, count 0) point at a row of a free bank group
                 const uint32_t addr = panel_s + (uint32_t)(ex[e] & 0x7fffffff) * (ST * 8) + h * 16;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
-                    double2 v = make_double2(0.0, 0.0);
-                    if (ex[e] >= 0) v = lds_f64x2(addr + j * 32);
+#if SWEEP_PAD_PRED
+                    lds_f64x2_unless_pad(bv[e][2 * j], bv[e][2 * j + 1], addr + j * 32, ex[e]);
+#else
+                    const double2 v = lds_f64x2(addr + j * 32);
                     bv[e][2 * j] = v.x;
                     bv[e][2 * j + 1] = v.y;
+#endif
                 }
             }
 #pragma unroll
@@ -140,7 +168,6 @@ sweep_kernel(const SweepArgs A)
 #pragma unroll
             for (int e = 0; e < 2; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 1);
             if (MODE == SWEEP_SHAPE) {
-                bool slow = false;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const double y = (double)ey[e];
@@ -150,6 +177,45 @@ sweep_kernel(const SweepArgs A)
                     for (int k = 0; k < D; ++k) acc[k] = fma(w, bv[e][k], acc[k]);
                     slow |= (!ok && ey[e] != 0);
                 }
+            }
+#else
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+#if SWEEP_PAD_PRED
+                double(&b1)[D] = bv[0];
+#else
+                double b1[D];
+#endif
+                const uint32_t addr = panel_s + (uint32_t)(ex[e] & 0x7fffffff) * (ST * 8) + h * 16;
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+#if SWEEP_PAD_PRED
+                    lds_f64x2_unless_pad(b1[2 * j], b1[2 * j + 1], addr + j * 32, ex[e]);
+#else
+                    const double2 v = lds_f64x2(addr + j * 32);
+                    b1[2 * j] = v.x;
+                    b1[2 * j + 1] = v.y;
+#endif
+                }
+                double s0 = a[0] * b1[0], s1 = a[1] * b1[1];
+#pragma unroll
+                for (int k = 2; k < D; k += 2) {
+                    s0 = fma(a[k], b1[k], s0);
+                    s1 = fma(a[k + 1], b1[k + 1], s1);
+                }
+                s[e] = s0 + s1;
+                s[e] += __shfl_xor_sync(0xffffffffu, s[e], 1);
+                if (MODE == SWEEP_SHAPE) {
+                    const double y = (double)ey[e];
+                    const bool ok = s[e] > TINY_NORMALIZER;
+                    const double w = ok ? div_pos(y, s[e]) : 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) acc[k] = fma(w, b1[k], acc[k]);
+                    slow |= (!ok && ey[e] != 0);
+                }
+            }
+#endif
+            if (MODE == SWEEP_SHAPE) {
                 if (slow && own >= 0) {
                     // log-space redo of an underflowed nonzero (hpf_numba.py:98-112); both lanes of
                     // the pair get here together.  Rare: kept rolled, costs the hot path no registers.
@@ -185,6 +251,7 @@ sweep_kernel(const SweepArgs A)
                 }
             }
             cur = nxt;
+            nxt = nxt2;
         }
     }
 
