@@ -331,3 +331,50 @@ def test_full_size_properties():
     assert_allclose(l0, np.mean(-p0), rtol=1e-12)                        # sweep llh == pointwise llh
     assert_allclose(l0, l1, rtol=1e-12)
     assert h0 == 0
+
+
+def test_two_shards_on_one_device_match_unsharded(g_cavi):
+    """Cell sharding algebra on one GPU: two engines, each with half the cells (nnz-balanced),
+    exchange buffers summed in rank order through the zero-copy torch view -- what
+    ShardedEngine does with NCCL -- must reproduce the unsharded golden run."""
+    import torch
+    from schpf_b200.engine import shard_bounds_by_nnz
+    g = _prep_capacity_shapes(g_cavi, "init_", 5)
+    C, G, K = 1000, 2000, 5
+    b = shard_bounds_by_nnz(np.bincount(g["row"], minlength=C), 2)
+    engines = []
+    for r in range(2):
+        lo, hi = int(b[r]), int(b[r + 1])
+        keep = (g["row"] >= lo) & (g["row"] < hi)
+        e = CaviEngine(hi - lo, G, K, row_offset=lo)
+        e.set_coo(g["row"][keep] - lo, g["col"][keep], g["data"][keep])
+        e.set_hyper(*[float(g[k]) for k in ("a", "ap", "bp", "c", "cp", "dp")])
+        e.set_state(theta=(g["init_theta_shp"][lo:hi], g["init_theta_rte"][lo:hi]),
+                    beta=(g["init_beta_shp"], g["init_beta_rte"]),
+                    xi=(g["init_xi_shp"][lo:hi], g["init_xi_rte"][lo:hi]),
+                    eta=(g["init_eta_shp"], g["init_eta_rte"]))
+        engines.append(e)
+    bufs = [e.exchange_tensor() for e in engines]
+    assert bufs[0].numel() == G * K + K and bufs[0].is_cuda and bufs[0].dtype == torch.float64
+    for t in range(10):
+        for e in engines:
+            e.step_begin()
+        total = bufs[0] + bufs[1]
+        for buf in bufs:
+            buf.copy_(total)
+        for e in engines:
+            e.step_end()
+    parts = [e.loss_parts() for e in engines]
+    loss = -(parts[0][0] + parts[1][0]) / (parts[0][1] + parts[1][1])
+    st = [e.get_state() for e in engines]
+    for e in engines:
+        e.close()
+    assert_equal(st[0]["beta"][0], st[1]["beta"][0])          # replicas stay bit-identical
+    assert_equal(st[0]["eta"][1], st[1]["eta"][1])
+    assert max_rel(st[0]["beta"][0], g["it10_beta_shp"]) < TOL and max_rel(st[0]["beta"][1], g["it10_beta_rte"]) < TOL
+    assert max_rel(np.concatenate([st[0]["theta"][0], st[1]["theta"][0]]), g["it10_theta_shp"]) < TOL
+    assert max_rel(np.concatenate([st[0]["theta"][1], st[1]["theta"][1]]), g["it10_theta_rte"]) < TOL
+    assert max_rel(np.concatenate([st[0]["xi"][1], st[1]["xi"][1]]), g["it10_xi_rte"]) < TOL
+    assert parts[0][1] + parts[1][1] == g["row"].shape[0]
+    # the golden loss list was taken at t = 0, 3, 6, 9: its last entry is the state after 10 iterations
+    assert_allclose(loss, g["it10_loss"][-1], rtol=1e-11)

@@ -1,0 +1,90 @@
+"""The cell-sharded path on CPU: two gloo ranks run schpf_b200.engine.ShardedEngine
+(the product's exchange logic) around oracle-backed local engines and must reproduce
+the unsharded golden run of the reference: same beta/eta on both ranks, theta/xi equal
+to the corresponding rows."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, GOLDEN
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir, freeze):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from schpf_b200.engine import ShardedEngine, shard_bounds_by_nnz
+    from oracle_engine import OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = dict(np.load(os.path.join(GOLDEN, "cavi_cfg1.npz")))
+    C, G = (int(v) for v in g["shape"])
+    K = g["init_theta_shp"].shape[1]
+    counts = np.bincount(g["row"], minlength=C)
+    b = shard_bounds_by_nnz(counts, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    keep = (g["row"] >= lo) & (g["row"] < hi)
+    local = OracleEngine(hi - lo, G, K)
+    local.set_coo(g["row"][keep] - lo, g["col"][keep], g["data"][keep])
+    local.set_hyper(*[float(g[k]) for k in ("a", "ap", "bp", "c", "cp", "dp")])
+    pre = "it50_" if freeze else "init_"
+    xi_shp = np.full(hi - lo, float(g["ap"]) + K * float(g["a"]))
+    eta_shp = g[pre + "eta_shp"] if freeze else np.full(G, float(g["cp"]) + K * float(g["c"]))
+    local.set_state(theta=(g["init_theta_shp"][lo:hi], g["init_theta_rte"][lo:hi]),
+                    beta=(g[pre + "beta_shp"], g[pre + "beta_rte"]),
+                    xi=(xi_shp, g["init_xi_rte"][lo:hi]), eta=(eta_shp, g[pre + "eta_rte"]))
+    eng = ShardedEngine(local, None)
+    loss = []
+    for t in range(10):
+        eng.step(1, freeze_genes=freeze)
+        if t % 3 == 0:
+            loss.append(eng.loss())
+    st = local.get_state()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), lo=lo, hi=hi, loss=np.array(loss),
+             **{n + s: st[n][i] for n in st for i, s in ((0, "_shp"), (1, "_rte"))})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("freeze", [False, True])
+def test_two_rank_gloo_matches_unsharded(tmp_path, freeze):
+    import torch.multiprocessing as mp
+    from oracle import hpf_numpy as onp
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path), freeze), nprocs=world, join=True)
+    g = dict(np.load(os.path.join(GOLDEN, "cavi_cfg1.npz")))
+    r = [dict(np.load(str(tmp_path / ("rank%d.npz" % k)))) for k in range(world)]
+    assert int(r[0]["lo"]) == 0 and int(r[0]["hi"]) == int(r[1]["lo"]) and int(r[1]["hi"]) == 1000
+    # nnz-balanced cut
+    counts = np.bincount(g["row"], minlength=1000)
+    assert abs(counts[:int(r[0]["hi"])].sum() - counts[int(r[0]["hi"]):].sum()) <= 2 * counts.max()
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.abs(b)))
+    if not freeze:
+        # replicas of the gene side are bit-identical across ranks and equal the reference's run
+        for n in ("beta_shp", "beta_rte", "eta_rte"):
+            assert np.array_equal(r[0][n], r[1][n])
+            assert rel(r[0][n], g["it10_" + n]) < 1e-11
+        for n in ("theta_shp", "theta_rte", "xi_rte"):
+            assert rel(np.concatenate([r[0][n], r[1][n]]), g["it10_" + n]) < 1e-11
+        assert np.allclose(r[0]["loss"], g["it10_loss"], rtol=1e-12) and np.array_equal(r[0]["loss"], r[1]["loss"])
+    else:
+        # projection: genes untouched, cells equal to an unsharded oracle projection
+        assert np.array_equal(r[0]["beta_shp"], g["it50_beta_shp"]) and np.array_equal(r[1]["eta_rte"], g["it50_eta_rte"])
+        st = onp.State(g["init_theta_shp"], g["init_theta_rte"], g["it50_beta_shp"], g["it50_beta_rte"],
+                       g["init_xi_shp"], g["init_xi_rte"], g["it50_eta_shp"], g["it50_eta_rte"])
+        hyp = [float(g[k]) for k in ("a", "ap", "bp", "c", "cp", "dp")]
+        onp.cavi_run(g["data"], g["row"], g["col"], st, *hyp, 10, freeze_genes=True)
+        assert rel(np.concatenate([r[0]["theta_shp"], r[1]["theta_shp"]]), st.theta_shp) < 1e-12
+        assert rel(np.concatenate([r[0]["xi_rte"], r[1]["xi_rte"]]), st.xi_rte) < 1e-12
