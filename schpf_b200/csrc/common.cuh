@@ -28,6 +28,15 @@ void set_error(const char *fmt, ...);
         if (rc__ != SCHPF_OK) return rc__;                                           \
     } while (0)
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with the
+// release threshold raised, so the multi-GB layout temporaries and per-fit buffers are
+// recycled between calls / fits instead of being mapped and unmapped every time.
+cudaError_t pool_malloc(void **p, size_t bytes, cudaStream_t stream);
+void pool_free(void *p, cudaStream_t stream);
+
+// SCHPF_TRACE=1: print host-side phase timings (synchronises the stream at each mark)
+void trace_mark(cudaStream_t stream, const char *what);
+
 // ------------------------------------------------------- table geometry ----
 // The sweep kernels give every nonzero to a PAIR of lanes; lane h of the pair
 // owns the 16-byte units {2j+h} of a K-row, so rows are padded to KP = a
@@ -184,6 +193,7 @@ struct SideLayout {
     int64_t *seg_ptr = nullptr;  // [(nblocks * W) * (npanel + 1)] in step pairs
     int4 *entries = nullptr;     // [total_pairs * 16] : {oth_local|pad, y, oth_local|pad, y}
     size_t bytes = 0;
+    cudaStream_t stream = nullptr;   // stream the buffers were allocated on (pool_free)
     void release();
 };
 

@@ -2,7 +2,10 @@
 // (schpf/scHPF_.py:642-715) with the count matrix and the eight variational
 // arrays resident in HBM.  See include/schpf_b200.h for the contract.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 #include <string>
 #include <vector>
@@ -26,6 +29,43 @@ void set_error(const char *fmt, ...)
 int sweep_ctas_per_sm(int K);
 int sweep_default_warps(int K);
 
+cudaError_t pool_malloc(void **p, size_t bytes, cudaStream_t stream)
+{
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev != configured_device) {
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        if (e != cudaSuccess) return e;
+        uint64_t keep = UINT64_MAX;      // never hand memory back to the OS between fits
+        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+        configured_device = dev;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, stream);
+}
+
+void pool_free(void *p, cudaStream_t stream)
+{
+    if (p) cudaFreeAsync(p, stream);
+}
+
+static thread_local cudaStream_t g_alloc_stream = nullptr;   // stream of the handle being served
+
+void trace_mark(cudaStream_t stream, const char *what)
+{
+    static const bool on = getenv("SCHPF_TRACE") != nullptr;
+    static auto last = std::chrono::steady_clock::now();
+    if (!on) return;
+    cudaStreamSynchronize(stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[schpf trace] %-28s %8.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
+
 }  // namespace schpf
 
 using namespace schpf;
@@ -40,7 +80,7 @@ struct schpf_engine {
     // options
     int opt_panel_rows = 0;     // 0 = largest that fits
     int opt_warps = 0;          // 0 = the most the register budget allows for this K
-    int opt_target_ctas = 2368; // 148 SMs x 2 CTAs x 8 waves
+    int opt_target_ctas = 4736; // 148 SMs x 2 CTAs x 16 waves
     int opt_variant = 0;
     int opt_timing = 0;
     int64_t row_offset = 0;     // global index of local cell 0 (random-phi stream)
@@ -54,6 +94,7 @@ struct schpf_engine {
     double *xi_shp = nullptr, *xi_rte = nullptr, *eta_shp = nullptr, *eta_rte = nullptr;
     // tables
     double *Et = nullptr, *Eb = nullptr;            // [C_pad x ST], [G_pad x ST]
+    double *Xt = nullptr, *Xb = nullptr;            // e_x tables in the same layout (llh sweep)
     double *elog_t = nullptr, *elog_b = nullptr;    // [C x K], [G x K]
     // accumulators: one allocation [acc_t | direct_t | acc_b | direct_b]
     double *accum = nullptr;
@@ -82,14 +123,14 @@ namespace {
 template <typename T>
 int dev_alloc(T **p, int64_t n)
 {
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(p), sizeof(T) * (size_t)(n > 0 ? n : 1)));
+    CUDA_TRY(pool_malloc(reinterpret_cast<void **>(p), sizeof(T) * (size_t)(n > 0 ? n : 1), g_alloc_stream));
     return SCHPF_OK;
 }
 
 template <typename T>
 void dev_free(T *&p)
 {
-    if (p) cudaFree(p);
+    if (p) pool_free(p, g_alloc_stream);
     p = nullptr;
 }
 
@@ -100,6 +141,7 @@ int check_handle(schpf_engine *h)
         return SCHPF_ERR_ARG;
     }
     CUDA_TRY(cudaSetDevice(h->device));
+    g_alloc_stream = h->stream;
     return SCHPF_OK;
 }
 
@@ -304,6 +346,7 @@ int download(double *dst, const double *src, int64_t n, cudaStream_t s)
 int finish_coo(schpf_engine *h)
 {
     // validate indices, take the data constant sum lgamma(y+1), build both layouts
+    trace_mark(h->stream, "coo copy");
     CUDA_TRY(cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream));
     RC_TRY(launch_validate_coo(h->stream, h->nnz, h->row, h->col, h->data, h->C, h->G, h->flag));
     int flag = 0;
@@ -326,25 +369,35 @@ int finish_coo(schpf_engine *h)
     const int64_t C_pad = ((h->C + Po - 1) / Po) * Po, G_pad = ((h->G + Po - 1) / Po) * Po;
     if (C_pad != h->C_pad || !h->Et) {
         dev_free(h->Et);
+        dev_free(h->Xt);
         RC_TRY(dev_alloc(&h->Et, C_pad * h->ST));
+        RC_TRY(dev_alloc(&h->Xt, C_pad * h->ST));
         h->C_pad = C_pad;
     }
     if (G_pad != h->G_pad || !h->Eb) {
         dev_free(h->Eb);
+        dev_free(h->Xb);
         RC_TRY(dev_alloc(&h->Eb, G_pad * h->ST));
+        RC_TRY(dev_alloc(&h->Xb, G_pad * h->ST));
         h->G_pad = G_pad;
     }
+    // pad rows / pad columns of the streamed tables stay zero for the lifetime of the layout
     CUDA_TRY(cudaMemsetAsync(h->Et, 0, sizeof(double) * (size_t)C_pad * h->ST, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->Eb, 0, sizeof(double) * (size_t)G_pad * h->ST, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->Xt, 0, sizeof(double) * (size_t)C_pad * h->ST, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->Xb, 0, sizeof(double) * (size_t)G_pad * h->ST, h->stream));
     h->tables_t_valid = h->tables_b_valid = false;
 
     int warps = sweep_default_warps(h->K);
     if (h->opt_warps > 0 && h->opt_warps < warps) warps = h->opt_warps;
+    trace_mark(h->stream, "validate + tables");
     RC_TRY(build_side_layout(h->cells, h->stream, h->nnz, h->row, h->col, h->data, h->C, h->G, Po, warps,
                              h->opt_target_ctas));
+    trace_mark(h->stream, "layout cells total");
     RC_TRY(build_side_layout(h->genes, h->stream, h->nnz, h->col, h->row, h->data, h->G, h->C, Po, warps,
                              h->opt_target_ctas));
 
+    trace_mark(h->stream, "layout genes total");
     int need = h->cells.nblocks * h->cells.nranges;
     if (need < 1024) need = 1024;
     if (need > h->partials_cap) {
@@ -356,6 +409,7 @@ int finish_coo(schpf_engine *h)
     CUDA_TRY(cudaMemcpyAsync(&h->lgamma_sum, h->scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->have_coo = true;
+    trace_mark(h->stream, "lgamma sum");
     return SCHPF_OK;
 }
 
@@ -398,6 +452,7 @@ int schpf_create(schpf_engine_t **out, int device, int64_t ncells, int64_t ngene
     schpf_engine *h = new schpf_engine();
     h->device = device;
     h->stream = reinterpret_cast<cudaStream_t>(stream);
+    g_alloc_stream = h->stream;
     h->C = ncells;
     h->G = ngenes;
     h->K = nfactors;
@@ -440,11 +495,12 @@ int schpf_destroy(schpf_engine_t *h)
 {
     if (!h) return SCHPF_OK;
     cudaSetDevice(h->device);
+    g_alloc_stream = h->stream;
     cudaStreamSynchronize(h->stream);
     free_coo(h);
     dev_free(h->theta_shp); dev_free(h->theta_rte); dev_free(h->beta_shp); dev_free(h->beta_rte);
     dev_free(h->xi_shp); dev_free(h->xi_rte); dev_free(h->eta_shp); dev_free(h->eta_rte);
-    dev_free(h->Et); dev_free(h->Eb); dev_free(h->elog_t); dev_free(h->elog_b);
+    dev_free(h->Et); dev_free(h->Eb); dev_free(h->Xt); dev_free(h->Xb); dev_free(h->elog_t); dev_free(h->elog_b);
     dev_free(h->accum); dev_free(h->exch); dev_free(h->colsum_b); dev_free(h->colsum_t_next);
     dev_free(h->partials); dev_free(h->scalars); dev_free(h->slow_hits); dev_free(h->flag);
     for (auto &e : h->ev_pool) {
@@ -472,8 +528,8 @@ int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value)
         set_error("unknown option '%s'", key);
         return SCHPF_ERR_ARG;
     }
-    if (h->opt_warps < 0 || h->opt_warps > 12) {
-        set_error("warps_per_cta must be in [0, 12] (0 = automatic)");
+    if (h->opt_warps < 0 || h->opt_warps > 16) {
+        set_error("warps_per_cta must be in [0, 16] (0 = automatic)");
         h->opt_warps = 0;
         return SCHPF_ERR_ARG;
     }
@@ -611,7 +667,7 @@ int schpf_step_with_xphi(schpf_engine_t *h, const double *xphi_host, int flags)
     if (rc == SCHPF_OK) rc = step_begin_impl(h, flags, 2, 0);
     if (rc == SCHPF_OK) rc = step_end_impl(h, flags);
     cudaStreamSynchronize(h->stream);
-    cudaFree(d_xphi);
+    pool_free(d_xphi, h->stream);
     return rc;
 }
 
@@ -654,40 +710,19 @@ int schpf_loss_parts(schpf_engine_t *h, double *sum_llh, int64_t *count)
     RC_TRY(check_handle(h));
     RC_TRY(require_ready(h));
     const int K = h->K;
-    // e_x tables in the sweep layout (hpf_numba.py:33-41); the factored tables are rebuilt afterwards
-    double *Xt = nullptr, *Xb = nullptr;
-    RC_TRY(dev_alloc(&Xt, h->C_pad * h->ST));
-    int rc = dev_alloc(&Xb, h->G_pad * h->ST);
-    if (rc == SCHPF_OK) {
-        cudaMemsetAsync(Xt, 0, sizeof(double) * (size_t)h->C_pad * h->ST, h->stream);
-        cudaMemsetAsync(Xb, 0, sizeof(double) * (size_t)h->G_pad * h->ST, h->stream);
-        rc = launch_ex_table(h->stream, h->C, K, h->theta_shp, h->theta_rte, Xt);
-    }
-    if (rc == SCHPF_OK) rc = launch_ex_table(h->stream, h->G, K, h->beta_shp, h->beta_rte, Xb);
+    // e_x tables in the sweep layout (hpf_numba.py:33-41)
+    RC_TRY(launch_ex_table(h->stream, h->C, K, h->theta_shp, h->theta_rte, h->Xt));
+    RC_TRY(launch_ex_table(h->stream, h->G, K, h->beta_shp, h->beta_rte, h->Xb));
+    SweepArgs A = side_args(h, h->cells);
+    A.own_tab = h->Xt;
+    A.oth_tab = h->Xb;
+    A.partial = h->partials;
+    RC_TRY(timed_sweep(h, SWEEP_LLH, h->cells, A));
+    RC_TRY(launch_sum_partials(h->stream, h->partials, h->cells.nblocks * h->cells.nranges, h->scalars));
+    h->n_launches += 3;
     double total = 0.0;
-    if (rc == SCHPF_OK) {
-        SweepArgs A = side_args(h, h->cells);
-        A.own_tab = Xt;
-        A.oth_tab = Xb;
-        A.partial = h->partials;
-        rc = timed_sweep(h, SWEEP_LLH, h->cells, A);
-        h->n_launches += 3;
-    }
-    if (rc == SCHPF_OK)
-        rc = launch_sum_partials(h->stream, h->partials, h->cells.nblocks * h->cells.nranges, h->scalars);
-    if (rc == SCHPF_OK) {
-        cudaError_t e = cudaMemcpyAsync(&total, h->scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) {
-            set_error("loss read-back -> %s", cudaGetErrorString(e));
-            rc = SCHPF_ERR_CUDA;
-        }
-    } else {
-        cudaStreamSynchronize(h->stream);
-    }
-    cudaFree(Xt);
-    cudaFree(Xb);
-    if (rc != SCHPF_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(&total, h->scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (sum_llh) *sum_llh = total - h->lgamma_sum;
     if (count) *count = h->nnz;
     return SCHPF_OK;
@@ -716,7 +751,7 @@ int schpf_llh_pointwise(schpf_engine_t *h, double *out_host_nnz)
                                   h->beta_shp, h->beta_rte, d);
     if (rc == SCHPF_OK) rc = download(out_host_nnz, d, h->nnz, h->stream);
     cudaStreamSynchronize(h->stream);
-    cudaFree(d);
+    pool_free(d, h->stream);
     return rc;
 }
 
@@ -731,7 +766,7 @@ int schpf_xphi_debug(schpf_engine_t *h, double *out)
                             nullptr);
     if (rc == SCHPF_OK) rc = download(out, d, h->nnz * h->K, h->stream);
     cudaStreamSynchronize(h->stream);
-    cudaFree(d);
+    pool_free(d, h->stream);
     return rc;
 }
 

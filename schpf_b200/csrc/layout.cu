@@ -40,10 +40,15 @@ constexpr int KEY_ROT_BITS = 2;
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
+// histogram of owner ids.  COO rows usually arrive sorted, i.e. whole warps hit one counter:
+// equal keys are combined inside the warp first (one atomic per distinct key and warp).
 __global__ void count_owners_kernel(int64_t nnz, const int32_t *__restrict__ own, int32_t *__restrict__ cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nnz) atomicAdd(cnt + own[i], 1);
+    if (i >= nnz) return;
+    const int32_t key = own[i];
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cnt + key, __popc(peers));
 }
 
 __global__ void iota_kernel(int64_t n, int32_t *p)
@@ -83,7 +88,10 @@ __global__ void make_keys_kernel(int64_t nnz, const int32_t *__restrict__ own, c
     keys[i] = ((uint64_t)seg << (KEY_LOCAL_BITS + KEY_ROT_BITS)) | ((uint64_t)cls << KEY_LOCAL_BITS) |
               (uint64_t)tl;
     vals[i] = ((uint64_t)(uint32_t)val[i] << 32) | (uint64_t)(uint32_t)tl;
-    atomicAdd(reinterpret_cast<unsigned long long *>(seg_cnt + seg * 4 + cls), 1ULL);
+    const int64_t list = seg * 4 + cls;
+    const unsigned peers = __match_any_sync(__activemask(), list);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1)
+        atomicAdd(reinterpret_cast<unsigned long long *>(seg_cnt + list), (unsigned long long)__popc(peers));
 }
 
 // ---- conflict-free schedule of one (quarter warp, panel) ----------------------
@@ -218,8 +226,9 @@ __global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__
 
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    cudaStream_t stream = nullptr;
+    ~DevBuf() { if (p) pool_free(p, stream); }
+    cudaError_t alloc(size_t bytes) { return pool_malloc(&p, bytes ? bytes : 1, stream); }
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
@@ -234,9 +243,9 @@ int bits_for(uint64_t max_value)
 
 void SideLayout::release()
 {
-    if (own_id) cudaFree(own_id);
-    if (seg_ptr) cudaFree(seg_ptr);
-    if (entries) cudaFree(entries);
+    if (own_id) pool_free(own_id, stream);
+    if (seg_ptr) pool_free(seg_ptr, stream);
+    if (entries) pool_free(entries, stream);
     own_id = nullptr;
     seg_ptr = nullptr;
     entries = nullptr;
@@ -272,10 +281,14 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     const int64_t n_seg = n_slots * L.npanel * 4;   // (slot, panel, bank group) lists
     const int64_t n_ptr = n_warps * (L.npanel + 1);
 
-    CUDA_TRY(cudaMalloc(&L.own_id, sizeof(int32_t) * n_slots));
-    CUDA_TRY(cudaMalloc(&L.seg_ptr, sizeof(int64_t) * n_ptr));
+    L.stream = stream;
+    CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&L.own_id), sizeof(int32_t) * n_slots, stream));
+    CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&L.seg_ptr), sizeof(int64_t) * n_ptr, stream));
 
     DevBuf cnt, ids, cnt_sorted, ids_sorted, slot_of, seg_cnt, seg_first, pairs, keys, vals, keys2, vals2, tmp, unplaced;
+    for (DevBuf *b : {&cnt, &ids, &cnt_sorted, &ids_sorted, &slot_of, &seg_cnt, &seg_first, &pairs, &keys, &vals,
+                      &keys2, &vals2, &tmp, &unplaced})
+        b->stream = stream;
     CUDA_TRY(unplaced.alloc(sizeof(int)));
     CUDA_TRY(cudaMemsetAsync(unplaced.p, 0, sizeof(int), stream));
     CUDA_TRY(cnt.alloc(sizeof(int32_t) * n_own));
@@ -291,6 +304,7 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     CUDA_TRY(keys2.alloc(sizeof(uint64_t) * nnz));
     CUDA_TRY(vals2.alloc(sizeof(uint64_t) * nnz));
 
+    trace_mark(stream, "  alloc");
     // 1. owners ranked by nonzero count, descending (stable: ties keep index order)
     CUDA_TRY(cudaMemsetAsync(cnt.p, 0, sizeof(int32_t) * n_own, stream));
     if (nnz > 0) count_owners_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(nnz, d_own, cnt.as<int32_t>());
@@ -317,15 +331,18 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     assign_slots_kernel<<<blocks_for(n_slots, 256), 256, 0, stream>>>(n_own, n_slots, ids_sorted.as<int32_t>(),
                                                                      slot_of.as<int32_t>(), L.own_id);
 
-    // 2. sort keys (slot, panel, rotated bank class, local index) and per-list counts
+    trace_mark(stream, "  owner ranking");
+    // 2. sort keys (slot, panel, bank group, local index) and per-list counts
     CUDA_TRY(cudaMemsetAsync(seg_cnt.p, 0, sizeof(int64_t) * n_seg, stream));
     if (nnz > 0) {
         make_keys_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(
             nnz, d_own, d_oth, d_val, slot_of.as<int32_t>(), panel_rows, L.npanel, keys.as<uint64_t>(),
             vals.as<uint64_t>(), seg_cnt.as<int64_t>());
+        trace_mark(stream, "  keys + counts");
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.as<uint64_t>(), keys2.as<uint64_t>(),
                                                  vals.as<uint64_t>(), vals2.as<uint64_t>(), nnz, 0, key_bits,
                                                  stream));
+        trace_mark(stream, "  radix sort");
     }
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, seg_cnt.as<int64_t>(), seg_first.as<int64_t>(), n_seg,
                                            stream));
@@ -341,9 +358,10 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     L.total_pairs = total_pairs;   // last column of every warp row is 0, so the last prefix is the total
     L.padded_entries = total_pairs * 2 * GROUPS_PER_WARP;
 
+    trace_mark(stream, "  scans + lengths");
     // 4. entry stream
     const int64_t n_int4 = total_pairs * GROUPS_PER_WARP;
-    CUDA_TRY(cudaMalloc(&L.entries, sizeof(int4) * (n_int4 > 0 ? n_int4 : 1)));
+    CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&L.entries), sizeof(int4) * (n_int4 > 0 ? n_int4 : 1), stream));
     if (n_int4 > 0) fill_pad_kernel<<<blocks_for(n_int4, 256), 256, 0, stream>>>(n_int4, L.entries);
     if (nnz > 0) {
         const int64_t n_qw = n_slots / 4;
@@ -352,6 +370,7 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
             reinterpret_cast<int2 *>(L.entries), unplaced.as<int>());
     }
     CUDA_TRY(cudaGetLastError());
+    trace_mark(stream, "  schedule + place");
     int n_unplaced = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_unplaced, unplaced.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));   // temporaries are freed on return

@@ -30,28 +30,31 @@ namespace schpf {
 
 namespace {
 
-constexpr int SWEEP_MAX_WARPS = 12;
+constexpr int SWEEP_MAX_WARPS = 16;
 
 // build-time experiment knobs (python -m schpf_b200.build reads SCHPF_NVCC_FLAGS)
 #ifndef SWEEP_INTERLEAVE
 #define SWEEP_INTERLEAVE 1
 #endif
 #ifndef SWEEP_W20
-#define SWEEP_W20 8
+#define SWEEP_W20 16
 #endif
 #ifndef SWEEP_PAD_PRED
 #define SWEEP_PAD_PRED 0
 #endif
+#ifndef SWEEP_MINCTA20
+#define SWEEP_MINCTA20 1
+#endif
 
-// A lane keeps 3*KP/2 doubles live (owner row, accumulators, streamed row) plus
-// ~44 registers of addressing: the CTA shape is picked per KP so that this fits
-// the register file without spilling (ptxas -v is checked in DESIGN.md §4).
-__host__ __device__ constexpr int sweep_min_ctas(int KP) { return KP <= 32 ? 2 : 1; }
+// A lane keeps 4*KP/2 doubles live (owner row, accumulators, the streamed rows of the two
+// steps in flight) plus ~45 registers of addressing.  One CTA per SM owns the whole shared
+// memory (the longer the per-owner lists of a panel, the less SELL padding: measured 24 % with
+// 720-row panels, 17 % with 1448), and the CTA is as many warps as the register file allows
+// without spilling (ptxas -v; registers are granted per SM sub-partition, so warps come in 4s).
+__host__ __device__ constexpr int sweep_min_ctas(int KP) { return KP == 20 ? SWEEP_MINCTA20 : 1; }
 __host__ __device__ constexpr int sweep_max_warps(int KP)
 {
-    // registers are granted per SM sub-partition (16384 each): what counts is warps per
-    // sub-partition, so CTA sizes are multiples of 4 warps where the budget is tight
-    return KP <= 12 ? 10 : KP <= 16 ? 8 : KP <= 20 ? SWEEP_W20 : KP <= 32 ? 6 : 8;
+    return KP == 20 ? SWEEP_W20 : KP <= 16 ? 16 : KP <= 32 ? 12 : 8;
 }
 
 template <int KP>
@@ -112,18 +115,30 @@ sweep_kernel(const SweepArgs A)
     const uint32_t panel_s = smem_u32(panel);
     const int64_t *sp = A.seg_ptr + (int64_t)wg * (A.npanel + 1);
 
+    // this warp's first panel: segment bounds and the first two entry pairs
+    int64_t i0 = 0, i1 = 0;
+    int4 cur = make_int4(0, 0, 0, 0), nxt = cur;
+    const int4 *ep = A.entries;
+    if (p0 < p1) {
+        i0 = sp[p0];
+        i1 = sp[p0 + 1];
+        ep = A.entries + i0 * GROUPS_PER_WARP + q;
+        if (i0 < i1) cur = ld_stream_int4(ep);
+        if (i0 + 1 < i1) nxt = ld_stream_int4(ep + GROUPS_PER_WARP);
+    }
+
     for (int p = p0; p < p1; ++p) {
         if (p > p0) __syncthreads();     // every warp is done with the previous panel
         if (tid == 0) {
             mbar_expect_tx(mbar, panel_bytes);
             bulk_g2s(panel, A.oth_tab + (int64_t)p * A.panel_rows * ST, panel_bytes, mbar);
         }
-        const int64_t i0 = sp[p], i1 = sp[p + 1];
-        const int4 *ep = A.entries + i0 * GROUPS_PER_WARP + q;
-        // the entry stream comes straight from HBM: keep two iterations in flight per lane
-        int4 cur = make_int4(0, 0, 0, 0), nxt = cur;
-        if (i0 < i1) cur = ld_stream_int4(ep);
-        if (i0 + 1 < i1) nxt = ld_stream_int4(ep + GROUPS_PER_WARP);
+        // bounds of the NEXT panel's segment, fetched while this panel is in flight
+        int64_t n0 = 0, n1 = 0;
+        if (p + 1 < p1) {
+            n0 = i1;                     // segments of consecutive panels are contiguous
+            n1 = sp[p + 2];
+        }
         mbar_wait(mbar, parity);
         parity ^= 1u;
 
@@ -253,6 +268,12 @@ sweep_kernel(const SweepArgs A)
             cur = nxt;
             nxt = nxt2;
         }
+        // first entries of the next panel: issued before the barrier so their latency overlaps it
+        i0 = n0;
+        i1 = n1;
+        ep = A.entries + i0 * GROUPS_PER_WARP + q;
+        if (i0 < i1) cur = ld_stream_int4(ep);
+        if (i0 + 1 < i1) nxt = ld_stream_int4(ep + GROUPS_PER_WARP);
     }
 
     if (MODE == SWEEP_SHAPE) {
@@ -333,7 +354,8 @@ size_t sweep_smem_bytes(int K, int panel_rows)
 int max_panel_rows(int K, int ctas_per_sm)
 {
     const int ST = stride_of_kp(kp_of(K));
-    const size_t per_cta = (size_t)(228 * 1024) / ctas_per_sm - 1024 - 64;
+    // 1 KB per CTA is reserved by the system; 256 B cover the mbarrier and the static reduction scratch
+    const size_t per_cta = (size_t)(228 * 1024) / ctas_per_sm - 1024 - 256;
     int rows = (int)(per_cta / ((size_t)ST * 8));
     rows &= ~3;
     if (rows > 4096) rows = 4096;   // 12-bit local index in the sort key
