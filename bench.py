@@ -54,7 +54,7 @@ class ClockSampler(object):
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=self.fh,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
