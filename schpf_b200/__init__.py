@@ -11,3 +11,4 @@ __version__ = "0.1.0"
 
 from .scHPF_ import (HPF_Gamma, scHPF, load_model, save_model,   # noqa: E402,F401
                      combine_across_cells)
+from .trials import run_trials, run_trials_pool                   # noqa: E402,F401

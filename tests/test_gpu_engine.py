@@ -378,3 +378,28 @@ def test_two_shards_on_one_device_match_unsharded(g_cavi):
     assert parts[0][1] + parts[1][1] == g["row"].shape[0]
     # the golden loss list was taken at t = 0, 3, 6, 9: its last entry is the state after 10 iterations
     assert_allclose(loss, g["it10_loss"][-1], rtol=1e-11)
+
+
+def test_run_trials_on_device(g_reinit, g_project, capsys):
+    """Model selection glue on the real engine: default loss (resident matrix), validation
+    cells (a nested projection at every check), reprojection, and the multi-K pool."""
+    from schpf_b200 import run_trials, run_trials_pool
+    X = _X(g_reinit)
+    np.random.seed(21)
+    best, others = run_trials(X, 3, ntrials=3, min_iter=4, max_iter=4, check_freq=2, verbose=False,
+                              return_all=True)
+    losses = [best.loss[-1]] + [m.loss[-1] for m in others]
+    assert losses == sorted(losses)
+    assert_allclose(best.loss[-1], onp.mean_negative_pois_llh(
+        g_reinit["data"], g_reinit["row"], g_reinit["col"], best.theta.vi_shape, best.theta.vi_rate,
+        best.beta.vi_shape, best.beta.vi_rate), rtol=0.05)         # last check is one iteration old
+    vcells = coo_matrix((g_reinit["data"][:400], (g_reinit["row"][:400] % 20, g_reinit["col"][:400])),
+                        shape=(20, X.shape[1]))
+    vcells.sum_duplicates()
+    np.random.seed(22)
+    m = run_trials(X, 3, ntrials=1, min_iter=3, max_iter=3, check_freq=1, verbose=False, vcells=vcells,
+                   reproject=True)
+    assert "train:" in capsys.readouterr().out and isinstance(m.loss[-1], list)
+    np.random.seed(5)
+    pool = run_trials_pool(X, [2, 3], ntrials=2, min_iter=3, max_iter=3, check_freq=1)
+    assert [p.nfactors for p in pool] == [2, 3] and all(np.isfinite(p.loss[-1]) for p in pool)

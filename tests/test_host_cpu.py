@@ -31,7 +31,11 @@ def _gam(g, name, prefix=""):
 
 @pytest.fixture()
 def oracle_backend(monkeypatch):
+    """Host logic under test, arithmetic from the oracle (tests only)."""
+    from oracle import hpf_numpy
+    import schpf_b200.loss
     monkeypatch.setattr(shell, "_engine_factory", OracleEngine)
+    monkeypatch.setattr(schpf_b200.loss, "compute_pois_llh", hpf_numpy.compute_pois_llh)
 
 
 # ---------------------------------------------------------------- C ABI ------
@@ -233,3 +237,40 @@ def test_shard_bounds_balance_nnz():
     # degenerate: all nonzeros in one cell, empty matrix
     assert list(shard_bounds_by_nnz([0, 0, 9, 0], 2)) in ([0, 2, 4], [0, 3, 4])
     assert list(shard_bounds_by_nnz([0, 0, 0], 2))[0] == 0
+
+
+# ------------------------------------------------------------ run_trials -----
+def test_run_trials_picks_lowest_loss_like_the_reference(oracle_backend, g_reinit, capsys):
+    from schpf_b200 import run_trials
+    X = _X(g_reinit)
+    np.random.seed(21)
+    best, others = run_trials(X, 3, ntrials=3, min_iter=4, max_iter=4, check_freq=2, verbose=False,
+                              return_all=True)
+    losses = [best.loss[-1]] + [m.loss[-1] for m in others]
+    assert losses == sorted(losses) and len(others) == 2
+    # the first trial consumes the RNG exactly like a plain seeded fit
+    np.random.seed(21)
+    first = scHPF(3, verbose=False, min_iter=4, max_iter=4, check_freq=2).fit(X)
+    assert any(np.array_equal(first.theta.vi_shape, m.theta.vi_shape) for m in [best] + others)
+    # validation cells: every check projects them (loss.py:37-102) and the training loss is printed
+    np.random.seed(22)
+    vcells = coo_matrix((g_reinit["data"][:400], (g_reinit["row"][:400] % 20, g_reinit["col"][:400])),
+                        shape=(20, X.shape[1]))
+    vcells.sum_duplicates()
+    m = run_trials(X, 3, ntrials=1, min_iter=3, max_iter=3, check_freq=1, verbose=False, vcells=vcells,
+                   reproject=True)
+    assert "train:" in capsys.readouterr().out
+    assert isinstance(m.loss[-1], list) and len(m.loss) == 4          # 3 checks + the reprojection's list
+
+
+def test_run_trials_pool_over_devices(oracle_backend, g_reinit):
+    from schpf_b200 import run_trials_pool
+    X = _X(g_reinit)
+    np.random.seed(5)
+    best, rejected = run_trials_pool(X, [2, 3], ntrials=2, min_iter=3, max_iter=3, check_freq=1,
+                                     return_all=True, devices=[0, 0])
+    assert [m.nfactors for m in best] == [2, 3] and [len(r) for r in rejected] == [1, 1]
+    assert all(b.loss[-1] <= r[0].loss[-1] for b, r in zip(best, rejected))
+    np.random.seed(5)
+    again = run_trials_pool(X, [2, 3], ntrials=2, min_iter=3, max_iter=3, check_freq=1, devices=[0])
+    assert all(np.array_equal(a.beta.vi_shape, b.beta.vi_shape) for a, b in zip(again, best))
