@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--panel-rows", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--target-ctas", type=int, default=0)
+    ap.add_argument("--torch-exchange", action="store_true",
+                    help="N>1: all-reduce through torch.distributed instead of the engine's own NCCL call")
     args = ap.parse_args()
     cfg = dict(CFG, cells_per_gpu=args.cells, genes=args.genes, draws_per_cell=args.draws, nfactors=args.factors)
     C, G, K, cf = cfg["cells_per_gpu"], cfg["genes"], cfg["nfactors"], cfg["check_freq"]
@@ -264,7 +266,7 @@ def main():
     layout_s = time.perf_counter() - t0
     local.set_hyper(HYPER["a"], HYPER["ap"], bp, HYPER["c"], HYPER["cp"], dp)
     local.set_state(**state)
-    engine = ShardedEngine(local, None) if world > 1 else local
+    engine = ShardedEngine(local, None, native=not args.torch_exchange) if world > 1 else local
 
     def run(n, t_start):
         """n CAVI iterations with the loss every cf-th, like _fit does"""
@@ -332,8 +334,9 @@ def main():
         "config": {"workload": workload, "nnz_total": nnz_total, "nnz_per_gpu": nnz_local, "check_freq": cf,
                    "l2_policy": "inputs_exceed_L2 (entry streams %.1f GB per sweep vs 126 MB L2)" %
                                 (info["padded_nnz_cells"] * 8 / 1e9),
-                   "parallelism": "cells sharded over %d GPU(s); one NCCL all-reduce of G*K+K doubles per iteration" % world
-                   if world > 1 else "single GPU",
+                   "parallelism": ("cells sharded over %d GPU(s); one NCCL all-reduce of G*K+K doubles per iteration, %s"
+                                   % (world, "torch.distributed" if args.torch_exchange else
+                                      "issued by the engine on its own stream")) if world > 1 else "single GPU",
                    "variant": "tiled two-pass sweep" if args.variant == 0 else "literal per-nnz atomics",
                    "layout": info, "layout_build_s": layout_s, "bp": bp, "dp": dp},
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
@@ -368,7 +371,7 @@ def main():
             loc.set_coo(hrow, hcol, hval)
             loc.set_hyper(HYPER["a"], HYPER["ap"], bp, HYPER["c"], HYPER["cp"], dp)
             loc.set_state(**state)
-            eng = ShardedEngine(loc, None)
+            eng = ShardedEngine(loc, None, native=not args.torch_exchange)
             n_checks = 0
             for t in range(e2e_iters):
                 eng.step(1)

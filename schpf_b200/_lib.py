@@ -48,6 +48,8 @@ SIGNATURES = {
     "schpf_step_begin": [c_vp, c_int, c_int, c_u64],
     "schpf_exchange_buffer": [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)],
     "schpf_step_end": [c_vp, c_int],
+    "schpf_comm_unique_id": [ctypes.c_char_p],
+    "schpf_comm_init": [c_vp, ctypes.c_char_p, c_int, c_int],
     "schpf_loss": [c_vp, p_dbl],
     "schpf_loss_parts": [c_vp, p_dbl, ctypes.POINTER(c_i64)],
     "schpf_llh_pointwise": [c_vp, p_dbl],

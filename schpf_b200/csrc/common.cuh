@@ -249,6 +249,7 @@ int launch_llh_pointwise(cudaStream_t s, int64_t nnz, int K, const int32_t *row,
 int launch_lgamma_sum(cudaStream_t s, int64_t nnz, const int32_t *data, double *partials, int nblk,
                       double *out);
 int launch_sum_partials(cudaStream_t s, const double *partials, int n, double *out);
+int launch_pack_loss(cudaStream_t s, const double *llh_sum, double lgamma_sum, double nnz, double *out2);
 int launch_validate_coo(cudaStream_t s, int64_t nnz, const int32_t *row, const int32_t *col,
                         const int32_t *data, int64_t C, int64_t G, int *flag);
 int launch_fill(cudaStream_t s, double *p, int64_t n, double v);

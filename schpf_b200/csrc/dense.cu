@@ -257,6 +257,14 @@ sum_partials_kernel(const double *__restrict__ partials, int n, double *__restri
     }
 }
 
+// out = [sum_i llh_i of this shard, its nnz]: the two scalars shards all-reduce at a loss check
+__global__ void pack_loss_kernel(const double *__restrict__ llh_sum, double lgamma_sum, double nnz,
+                                 double *__restrict__ out2)
+{
+    out2[0] = *llh_sum - lgamma_sum;
+    out2[1] = nnz;
+}
+
 __global__ void validate_coo_kernel(int64_t nnz, const int32_t *__restrict__ row,
                                     const int32_t *__restrict__ col, const int32_t *__restrict__ data,
                                     int64_t C, int64_t G, int *flag)
@@ -424,6 +432,13 @@ int launch_lgamma_sum(cudaStream_t s, int64_t nnz, const int32_t *data, double *
 int launch_sum_partials(cudaStream_t s, const double *partials, int n, double *out)
 {
     sum_partials_kernel<<<1, DENSE_THREADS, 0, s>>>(partials, n, out);
+    LAUNCH_CHECK();
+    return SCHPF_OK;
+}
+
+int launch_pack_loss(cudaStream_t s, const double *llh_sum, double lgamma_sum, double nnz, double *out2)
+{
+    pack_loss_kernel<<<1, 1, 0, s>>>(llh_sum, lgamma_sum, nnz, out2);
     LAUNCH_CHECK();
     return SCHPF_OK;
 }

@@ -1,6 +1,7 @@
 // Engine-level C ABI: the loop body of the reference's scHPF._fit
 // (schpf/scHPF_.py:642-715) with the count matrix and the eight variational
 // arrays resident in HBM.  See include/schpf_b200.h for the contract.
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -70,6 +71,53 @@ void trace_mark(cudaStream_t stream, const char *what)
 
 using namespace schpf;
 
+// ---- NCCL, bound at run time (no link-time dependency) -----------------------
+namespace {
+struct NcclId128 {          // layout of ncclUniqueId (nccl.h: char internal[128]), passed by value
+    char b[128];
+};
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *id) = nullptr;
+    int (*CommInitRank)(void **comm, int nranks, NcclId128 id, int rank) = nullptr;
+    int (*AllReduce)(const void *send, void *recv, size_t count, int dtype, int op, void *comm,
+                     cudaStream_t stream) = nullptr;
+    int (*CommDestroy)(void *comm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+typedef decltype(NcclApi::CommInitRank) comm_init_fn;
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // nccl.h: ncclFloat64, ncclSum
+
+int load_nccl()
+{
+    if (g_nccl.lib) return SCHPF_OK;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+        set_error("dlopen(libnccl.so.2) failed: %s", dlerror());
+        return SCHPF_ERR_STATE;
+    }
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<comm_init_fn>(dlsym(lib, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        set_error("libnccl.so.2 lacks an expected symbol");
+        return SCHPF_ERR_STATE;
+    }
+    g_nccl.lib = lib;
+    return SCHPF_OK;
+}
+
+int nccl_check(int rc, const char *what)
+{
+    if (rc == 0) return SCHPF_OK;
+    set_error("%s -> NCCL error %d (%s)", what, rc, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return SCHPF_ERR_CUDA;
+}
+}  // namespace
+
 struct schpf_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -110,6 +158,10 @@ struct schpf_engine {
 
     int32_t *row = nullptr, *col = nullptr, *data = nullptr;
     SideLayout cells, genes;
+
+    // cell sharding with the exchange done by the engine (schpf_comm_init)
+    void *comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
 
     // counters
     double n_iterations = 0, n_sweeps = 0, n_launches = 0;
@@ -497,6 +549,8 @@ int schpf_destroy(schpf_engine_t *h)
     cudaSetDevice(h->device);
     g_alloc_stream = h->stream;
     cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
     free_coo(h);
     dev_free(h->theta_shp); dev_free(h->theta_rte); dev_free(h->beta_shp); dev_free(h->beta_rte);
     dev_free(h->xi_shp); dev_free(h->xi_rte); dev_free(h->eta_shp); dev_free(h->eta_rte);
@@ -635,12 +689,22 @@ int schpf_get_state(schpf_engine_t *h, double *theta_shp, double *theta_rte, dou
     return SCHPF_OK;
 }
 
+// the one exchange step of an iteration, when the engine owns the communicator
+static int exchange_if_sharded(schpf_engine_t *h, int flags)
+{
+    if (!h->comm || (flags & SCHPF_FREEZE_GENES)) return SCHPF_OK;
+    return nccl_check(g_nccl.AllReduce(h->exch, h->exch, (size_t)(h->G * h->K + h->K), NCCL_FLOAT64, NCCL_SUM,
+                                       h->comm, h->stream),
+                      "ncclAllReduce(exchange buffer)");
+}
+
 int schpf_step(schpf_engine_t *h, int n_iters, int flags)
 {
     RC_TRY(check_handle(h));
     RC_TRY(require_ready(h));
     for (int t = 0; t < n_iters; ++t) {
         RC_TRY(step_begin_impl(h, flags, 0, 0));
+        RC_TRY(exchange_if_sharded(h, flags));
         RC_TRY(step_end_impl(h, flags));
     }
     return SCHPF_OK;
@@ -665,6 +729,7 @@ int schpf_step_with_xphi(schpf_engine_t *h, const double *xphi_host, int flags)
     if (rc == SCHPF_OK && !freeze)
         rc = launch_scatter_xphi(h->stream, h->nnz, h->K, d_xphi, h->col, h->direct_b);
     if (rc == SCHPF_OK) rc = step_begin_impl(h, flags, 2, 0);
+    if (rc == SCHPF_OK) rc = exchange_if_sharded(h, flags);
     if (rc == SCHPF_OK) rc = step_end_impl(h, flags);
     cudaStreamSynchronize(h->stream);
     pool_free(d_xphi, h->stream);
@@ -676,6 +741,7 @@ int schpf_step_random_phi(schpf_engine_t *h, uint64_t seed, int flags)
     RC_TRY(check_handle(h));
     RC_TRY(require_ready(h));
     RC_TRY(step_begin_impl(h, flags, 1, seed));
+    RC_TRY(exchange_if_sharded(h, flags));
     return step_end_impl(h, flags);
 }
 
@@ -720,11 +786,23 @@ int schpf_loss_parts(schpf_engine_t *h, double *sum_llh, int64_t *count)
     RC_TRY(timed_sweep(h, SWEEP_LLH, h->cells, A));
     RC_TRY(launch_sum_partials(h->stream, h->partials, h->cells.nblocks * h->cells.nranges, h->scalars));
     h->n_launches += 3;
-    double total = 0.0;
-    CUDA_TRY(cudaMemcpyAsync(&total, h->scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (sum_llh) *sum_llh = total - h->lgamma_sum;
-    if (count) *count = h->nnz;
+    double pair[2] = {0.0, 0.0};
+    if (h->comm) {
+        // [sum_i llh_i of this shard, nnz of this shard] summed over shards (2 doubles)
+        RC_TRY(launch_pack_loss(h->stream, h->scalars, h->lgamma_sum, (double)h->nnz, h->scalars + 2));
+        RC_TRY(nccl_check(g_nccl.AllReduce(h->scalars + 2, h->scalars + 2, 2, NCCL_FLOAT64, NCCL_SUM, h->comm,
+                                           h->stream),
+                          "ncclAllReduce(loss)"));
+        CUDA_TRY(cudaMemcpyAsync(pair, h->scalars + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(pair, h->scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        pair[0] -= h->lgamma_sum;
+        pair[1] = (double)h->nnz;
+    }
+    if (sum_llh) *sum_llh = pair[0];
+    if (count) *count = (int64_t)(pair[1] + 0.5);
     return SCHPF_OK;
 }
 
@@ -768,6 +846,36 @@ int schpf_xphi_debug(schpf_engine_t *h, double *out)
     cudaStreamSynchronize(h->stream);
     pool_free(d, h->stream);
     return rc;
+}
+
+int schpf_comm_unique_id(char *id128_out)
+{
+    if (!id128_out) {
+        set_error("null id buffer");
+        return SCHPF_ERR_ARG;
+    }
+    RC_TRY(load_nccl());
+    return nccl_check(g_nccl.GetUniqueId(id128_out), "ncclGetUniqueId");
+}
+
+int schpf_comm_init(schpf_engine_t *h, const char *id128, int rank, int world_size)
+{
+    RC_TRY(check_handle(h));
+    if (!id128 || world_size < 1 || rank < 0 || rank >= world_size) {
+        set_error("bad communicator arguments (rank %d of %d)", rank, world_size);
+        return SCHPF_ERR_ARG;
+    }
+    RC_TRY(load_nccl());
+    if (h->comm) {
+        g_nccl.CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    NcclId128 id;
+    memcpy(id.b, id128, 128);
+    RC_TRY(nccl_check(g_nccl.CommInitRank(&h->comm, world_size, id, rank), "ncclCommInitRank"));
+    h->comm_rank = rank;
+    h->comm_world = world_size;
+    return SCHPF_OK;
 }
 
 int schpf_synchronize(schpf_engine_t *h)
