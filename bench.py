@@ -34,6 +34,16 @@ CFG = dict(cells_per_gpu=100000, genes=20000, draws_per_cell=2000, nfactors=20, 
 HYPER = dict(a=0.3, ap=1.0, c=0.3, cp=1.0)
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """progress to stderr (SCHPF_BENCH_VERBOSE=1): where a multi-rank run is, and when"""
+    if os.environ.get("SCHPF_BENCH_VERBOSE"):
+        sys.stderr.write("[bench r%s +%.1fs] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -216,6 +226,9 @@ def emit(obj):
 
 def main():
     quiet_stdout()
+    # a hung collective must not hang the box: dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(env_int("SCHPF_BENCH_WATCHDOG_S", 420), exit=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -258,6 +271,7 @@ def main():
     device = "cuda:%d" % local_rank
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
+    log("process group up")
 
     def barrier():
         if world > 1:
@@ -267,6 +281,7 @@ def main():
     reduce_sum = (lambda t: dist.all_reduce(t)) if world > 1 else None
     row, col, val = make_problem(torch, device, rank, cfg)
     nnz_local = int(row.numel())
+    log("synthetic shard ready: nnz %d" % nnz_local)
     bp, dp = empirical_hypers(torch, row, col, val, C, G, reduce_sum)
     state = init_state(C, G, K, bp, dp, rank)
     nnz_t = torch.tensor([float(nnz_local)], dtype=torch.float64, device=device)
@@ -287,9 +302,11 @@ def main():
     local.set_coo(row, col, val)
     torch.cuda.synchronize()
     layout_s = time.perf_counter() - t0
+    log("layout built in %.2fs" % layout_s)
     local.set_hyper(HYPER["a"], HYPER["ap"], bp, HYPER["c"], HYPER["cp"], dp)
     local.set_state(**state)
     engine = ShardedEngine(local, None, native=not args.torch_exchange) if world > 1 else local
+    log("engine ready (exchange: %s)" % ("single GPU" if world == 1 else "native" if engine.native else "torch"))
 
     def run(n, t_start):
         """n CAVI iterations with the loss every cf-th, like _fit does"""
@@ -301,6 +318,7 @@ def main():
         return losses
 
     run(warmup, 0)
+    log("warm-up done")
     barrier()
     local.counter("reset")
     sampler = ClockSampler(local_rank)
@@ -312,6 +330,7 @@ def main():
     losses = run(steps, warmup)
     e1.record()
     barrier()
+    log("timed region done")
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -372,7 +391,9 @@ def main():
         hcol = torch.empty(nnz_local, dtype=torch.int32, pin_memory=True).copy_(col)
         hval = torch.empty(nnz_local, dtype=torch.int32, pin_memory=True).copy_(val)
         torch.cuda.synchronize()
+        log("pinned host copy of the shard ready")
         local.close()
+        log("first engine closed")
         del row, col, val
         torch.cuda.empty_cache()
         e2e_iters = steps
@@ -404,6 +425,7 @@ def main():
             loc.get_state()
             barrier()
             e2e_s = time.perf_counter() - t0
+            log("e2e loop done")
             loc.close()
         ts = torch.tensor([e2e_s], dtype=torch.float64, device=device)
         if world > 1:
@@ -424,11 +446,12 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         result["cpu_baseline"] = cpu_reference_run(*cpu_src, min(args.cpu_cells, C), G, K, bp, dp, state, n_iter=3)
 
+    if rank == 0:
+        emit(result)
+    log("result emitted")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if rank == 0:
-        emit(result)
 
 
 def main_reference(args, cfg, rank, world, workload):
