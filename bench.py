@@ -450,8 +450,11 @@ def main():
         emit(result)
     log("result emitted")
     if world > 1:
+        # leave without tearing communicators down: teardown order between torch's NCCL
+        # communicator and the engine's is not worth a hang at exit
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main_reference(args, cfg, rank, world, workload):

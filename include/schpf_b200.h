@@ -154,15 +154,19 @@ int schpf_step_begin(schpf_engine_t *h, int flags, int mode, uint64_t seed);
 int schpf_exchange_buffer(schpf_engine_t *h, void **device_ptr, int64_t *n_doubles);
 int schpf_step_end(schpf_engine_t *h, int flags);
 
-/* Optional: let the engine run the exchange itself.  After schpf_comm_init every
- * schpf_step* call of this handle performs the all-reduce (ncclAllReduce, sum, fp64,
- * in place on the exchange buffer) IN ORDER ON THE ENGINE'S OWN STREAM between its two
- * phases, and schpf_loss* returns the loss over all shards.  NCCL is loaded with
- * dlopen("libnccl.so.2") at first use; `id128` is the 128-byte ncclUniqueId produced by
- * schpf_comm_unique_id on rank 0 and distributed by the host framework.  Collective
- * calls: every rank must make the same sequence of step / loss calls.            */
+/* Optional: let the engine run the exchange itself.  A communicator (one per process and
+ * group of ranks; creating one takes seconds, so the host framework keeps it and shares it
+ * between successive engines) is created from the 128-byte ncclUniqueId that
+ * schpf_comm_unique_id produced on rank 0 and the host framework distributed.  After
+ * schpf_comm_attach every schpf_step* call of that handle performs the all-reduce
+ * (ncclAllReduce, sum, fp64, in place on the exchange buffer) IN ORDER ON THE ENGINE'S OWN
+ * STREAM between its two phases, and schpf_loss* returns the loss over all shards.  NCCL is
+ * loaded with dlopen("libnccl.so.2") at first use.  Collective calls: every rank must make
+ * the same sequence of create / step / loss calls.  The engine does not own the communicator. */
 int schpf_comm_unique_id(char *id128_out);
-int schpf_comm_init(schpf_engine_t *h, const char *id128, int rank, int world_size);
+int schpf_comm_create(void **comm_out, int device, const char *id128, int rank, int world_size);
+int schpf_comm_destroy(void *comm);
+int schpf_comm_attach(schpf_engine_t *h, void *comm);    /* comm == NULL detaches */
 
 /* loss.py:142-168 mean_negative_pois_llh of the resident matrix under the
  * resident state.  `sum_llh` receives sum_i llh_i and `count` the number of

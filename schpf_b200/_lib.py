@@ -49,7 +49,9 @@ SIGNATURES = {
     "schpf_exchange_buffer": [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)],
     "schpf_step_end": [c_vp, c_int],
     "schpf_comm_unique_id": [ctypes.c_char_p],
-    "schpf_comm_init": [c_vp, ctypes.c_char_p, c_int, c_int],
+    "schpf_comm_create": [ctypes.POINTER(c_vp), c_int, ctypes.c_char_p, c_int, c_int],
+    "schpf_comm_destroy": [c_vp],
+    "schpf_comm_attach": [c_vp, c_vp],
     "schpf_loss": [c_vp, p_dbl],
     "schpf_loss_parts": [c_vp, p_dbl, ctypes.POINTER(c_i64)],
     "schpf_llh_pointwise": [c_vp, p_dbl],

@@ -159,9 +159,8 @@ struct schpf_engine {
     int32_t *row = nullptr, *col = nullptr, *data = nullptr;
     SideLayout cells, genes;
 
-    // cell sharding with the exchange done by the engine (schpf_comm_init)
+    // cell sharding with the exchange done by the engine (schpf_comm_attach; not owned)
     void *comm = nullptr;
-    int comm_rank = 0, comm_world = 1;
 
     // counters
     double n_iterations = 0, n_sweeps = 0, n_launches = 0;
@@ -549,8 +548,7 @@ int schpf_destroy(schpf_engine_t *h)
     cudaSetDevice(h->device);
     g_alloc_stream = h->stream;
     cudaStreamSynchronize(h->stream);
-    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    h->comm = nullptr;
+    h->comm = nullptr;       // not owned
     free_coo(h);
     dev_free(h->theta_shp); dev_free(h->theta_rte); dev_free(h->beta_shp); dev_free(h->beta_rte);
     dev_free(h->xi_shp); dev_free(h->xi_rte); dev_free(h->eta_shp); dev_free(h->eta_rte);
@@ -858,23 +856,32 @@ int schpf_comm_unique_id(char *id128_out)
     return nccl_check(g_nccl.GetUniqueId(id128_out), "ncclGetUniqueId");
 }
 
-int schpf_comm_init(schpf_engine_t *h, const char *id128, int rank, int world_size)
+int schpf_comm_create(void **comm_out, int device, const char *id128, int rank, int world_size)
 {
-    RC_TRY(check_handle(h));
-    if (!id128 || world_size < 1 || rank < 0 || rank >= world_size) {
+    if (!comm_out || !id128 || world_size < 1 || rank < 0 || rank >= world_size) {
         set_error("bad communicator arguments (rank %d of %d)", rank, world_size);
         return SCHPF_ERR_ARG;
     }
+    *comm_out = nullptr;
+    CUDA_TRY(cudaSetDevice(device));
     RC_TRY(load_nccl());
-    if (h->comm) {
-        g_nccl.CommDestroy(h->comm);
-        h->comm = nullptr;
-    }
     NcclId128 id;
     memcpy(id.b, id128, 128);
-    RC_TRY(nccl_check(g_nccl.CommInitRank(&h->comm, world_size, id, rank), "ncclCommInitRank"));
-    h->comm_rank = rank;
-    h->comm_world = world_size;
+    return nccl_check(g_nccl.CommInitRank(comm_out, world_size, id, rank), "ncclCommInitRank");
+}
+
+int schpf_comm_destroy(void *comm)
+{
+    if (!comm) return SCHPF_OK;
+    RC_TRY(load_nccl());
+    return nccl_check(g_nccl.CommDestroy(comm), "ncclCommDestroy");
+}
+
+int schpf_comm_attach(schpf_engine_t *h, void *comm)
+{
+    RC_TRY(check_handle(h));
+    if (comm) RC_TRY(load_nccl());
+    h->comm = comm;
     return SCHPF_OK;
 }
 

@@ -144,11 +144,19 @@ class CaviEngine(object):
         _lib.check(_lib.load().schpf_comm_unique_id(buf))
         return buf.raw
 
-    def comm_init(self, unique_id, rank, world_size):
-        """Join the communicator: from now on step()/loss() include the all-reduce, enqueued
-        in order on this engine's stream (collective: all ranks call the same sequence)."""
+    @staticmethod
+    def comm_create(unique_id, rank, world_size, device):
+        """Open this process's NCCL communicator (seconds; keep it and share it between engines)."""
         assert len(unique_id) == 128
-        _lib.check(self._lib.schpf_comm_init(self._h, unique_id, c_int(int(rank)), c_int(int(world_size))))
+        comm = c_vp()
+        _lib.check(_lib.load().schpf_comm_create(ctypes.byref(comm), c_int(int(device)), unique_id,
+                                                 c_int(int(rank)), c_int(int(world_size))))
+        return comm
+
+    def comm_attach(self, comm):
+        """From now on step()/loss() include the all-reduce, enqueued in order on this engine's
+        stream (collective: all ranks call the same sequence).  The engine does not own `comm`."""
+        _lib.check(self._lib.schpf_comm_attach(self._h, comm))
 
     def exchange_buffer(self):
         """(device pointer, number of doubles) of the per-iteration exchange buffer."""
@@ -243,14 +251,24 @@ class ShardedEngine(object):
         self._dist = dist
         self._buf = None
         if native is None:
-            native = hasattr(local, "comm_init") and dist.get_backend(group) == "nccl"
+            native = hasattr(local, "comm_attach") and dist.get_backend(group) == "nccl"
         self.native = bool(native)
         if self.native:
+            local.comm_attach(self._communicator(local, group))
+
+    _comms = {}     # (group, device) -> communicator: created once per process, like torch's own
+
+    @classmethod
+    def _communicator(cls, local, group):
+        import torch.distributed as dist
+        key = (group, local.device)
+        if key not in cls._comms:
             rank, world = dist.get_rank(group), dist.get_world_size(group)
             box = [local.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0,
                                        group=group)
-            local.comm_init(box[0], rank, world)
+            cls._comms[key] = local.comm_create(box[0], rank, world, local.device)
+        return cls._comms[key]
 
     def _exchange(self):
         if self._buf is None:
