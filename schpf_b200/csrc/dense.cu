@@ -14,6 +14,13 @@ constexpr int DENSE_WARPS = DENSE_THREADS / 32;
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
+// one warp per row, rows strided over a grid of at most 148 SMs x 8 CTAs
+inline int finalize_grid(int64_t n)
+{
+    const int64_t want = (n + (256 / 32) - 1) / (256 / 32);
+    return (int)(want < 1 ? 1 : want > 148 * 8 ? 148 * 8 : want);
+}
+
 // column sums of per-thread values over the block, then one atomicAdd per k
 // per block (K <= 64).  `val(k)` returns this thread's contribution.
 template <typename F>
@@ -34,7 +41,7 @@ __device__ __forceinline__ void block_colsum_atomic(int K, F val, double *colsum
     }
 }
 
-// One thread per row of a (n x K) Gamma family.
+// One WARP per row of a (n x K) Gamma family, lanes over the factors (K <= 64: two per lane).
 //   UPDATE: shp = prior_shape + v,  rte = cap_shp/cap_rte(old) + other_colsum[k],
 //           cap_rte = prior_rate + sum_k shp/rte
 //     beta : scHPF_.py:699-704 (hpf_numba.py:129-156, :160-177)   v = sum over the gene's nonzeros
@@ -42,6 +49,9 @@ __device__ __forceinline__ void block_colsum_atomic(int K, F val, double *colsum
 //   always: elog = psi(shp) - log(rte)  (hpf_numba.py:83-94, scHPF_.py:108-111),
 //           E = exp(elog - max_k elog)  (factored softmax table),
 //           colsum_out[k] += shp/rte    (the sum at hpf_numba.py:167-170 for the NEXT rate update)
+// Row accesses are coalesced, the digamma / log / exp chains of a row run in parallel, the
+// row-wise sum and max are warp shuffles, and each lane carries its own column's partial sum
+// over the rows its warp visits (one atomicAdd per lane and warp at the end).
 template <bool UPDATE>
 __global__ void __launch_bounds__(DENSE_THREADS)
 finalize_kernel(int64_t n, int K, int ST, double prior_shape, double prior_rate,
@@ -51,36 +61,61 @@ finalize_kernel(int64_t n, int K, int ST, double prior_shape, double prior_rate,
                 double *__restrict__ shp, double *__restrict__ rte, double *__restrict__ elog,
                 double *__restrict__ Etab, double *__restrict__ colsum_out)
 {
-    const int64_t i = (int64_t)blockIdx.x * DENSE_THREADS + threadIdx.x;
-    const bool live = i < n;
-    if (live) {
-        double *s = shp + i * K, *r = rte + i * K, *el = elog + i * K, *E = Etab + i * (int64_t)ST;
-        if (UPDATE) {
-            const double cap_ex = cap_shp[i] / cap_rte[i];
-            double sum_ex = 0.0;
-            for (int k = 0; k < K; ++k) {
-                double v;
-                if (folded) v = folded[i * K + k];
-                else v = fma(E[k], acc[i * K + k], direct[i * K + k]);
-                const double sk = prior_shape + v;
-                const double rk = cap_ex + other_colsum[k];
-                s[k] = sk;
-                r[k] = rk;
-                sum_ex += sk / rk;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * DENSE_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * DENSE_THREADS) >> 5;
+    double col[2] = {0.0, 0.0};
+    double oc[2] = {0.0, 0.0};
+    if (UPDATE) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            if (lane + 32 * t < K) oc[t] = other_colsum[lane + 32 * t];
+    }
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        double sk[2] = {1.0, 1.0}, rk[2] = {1.0, 1.0}, el[2];
+        double sum_ex = 0.0, m = -INFINITY;
+        const double cap_ex = UPDATE ? cap_shp[i] / cap_rte[i] : 0.0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int k = lane + 32 * t;
+            el[t] = -INFINITY;
+            if (k < K) {
+                if (UPDATE) {
+                    double v;
+                    if (folded) v = folded[i * K + k];
+                    else v = fma(Etab[i * (int64_t)ST + k], acc[i * K + k], direct[i * K + k]);
+                    sk[t] = prior_shape + v;
+                    rk[t] = cap_ex + oc[t];
+                    shp[i * K + k] = sk[t];
+                    rte[i * K + k] = rk[t];
+                } else {
+                    sk[t] = shp[i * K + k];
+                    rk[t] = rte[i * K + k];
+                }
+                const double ex = sk[t] / rk[t];
+                sum_ex += ex;
+                col[t] += ex;
+                el[t] = digamma_pos(sk[t]) - log(rk[t]);
+                elog[i * K + k] = el[t];
+                m = fmax(m, el[t]);
             }
-            cap_rte[i] = prior_rate + sum_ex;
         }
-        double m = -INFINITY;
-        for (int k = 0; k < K; ++k) {
-            const double e = digamma_pos(s[k]) - log(r[k]);
-            el[k] = e;
-            m = fmax(m, e);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (UPDATE) {
+            sum_ex = warp_sum(sum_ex);
+            if (lane == 0) cap_rte[i] = prior_rate + sum_ex;
         }
-        for (int k = 0; k < K; ++k) E[k] = exp(el[k] - m);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int k = lane + 32 * t;
+            if (k < K) Etab[i * (int64_t)ST + k] = exp(el[t] - m);
+        }
     }
     if (colsum_out) {
-        block_colsum_atomic(
-            K, [&](int k) { return live ? shp[i * K + k] / rte[i * K + k] : 0.0; }, colsum_out);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            if (lane + 32 * t < K) atomicAdd(colsum_out + lane + 32 * t, col[t]);
     }
 }
 
@@ -341,7 +376,7 @@ int launch_prep_side(cudaStream_t s, int64_t n, int K, const double *shp, const 
 {
     if (n <= 0) return SCHPF_OK;
     const int ST = stride_of_kp(kp_of(K));
-    finalize_kernel<false><<<blocks_for(n, DENSE_THREADS), DENSE_THREADS, 0, s>>>(
+    finalize_kernel<false><<<finalize_grid(n), DENSE_THREADS, 0, s>>>(
         n, K, ST, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
         const_cast<double *>(shp), const_cast<double *>(rte), elog, E, colsum);
     LAUNCH_CHECK();
@@ -356,7 +391,7 @@ int launch_finalize(cudaStream_t s, int64_t n, int K, double prior_shape, double
     if (n <= 0) return SCHPF_OK;
     (void)E;  // the factored table read for the fold is the one being rewritten (Etab)
     const int ST = stride_of_kp(kp_of(K));
-    finalize_kernel<true><<<blocks_for(n, DENSE_THREADS), DENSE_THREADS, 0, s>>>(
+    finalize_kernel<true><<<finalize_grid(n), DENSE_THREADS, 0, s>>>(
         n, K, ST, prior_shape, prior_rate, folded, acc, direct, other_colsum, cap_shp, cap_rte, shp,
         rte, elog, Etab, colsum_out);
     LAUNCH_CHECK();

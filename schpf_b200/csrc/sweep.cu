@@ -258,12 +258,13 @@ sweep_kernel(const SweepArgs A)
                     }
                 }
             } else {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    // hpf_numba.py:49-50 without the lgamma term (a constant of the data)
-                    const double v = fma((double)ey[e], log(s[e]), -s[e]);
-                    if (ex[e] >= 0 && h == 0) llh += v;
-                }
+                // hpf_numba.py:49-50 without the lgamma term (a constant of the data).  Both lanes of
+                // a pair hold both normalisers: lane 0 finishes step 0, lane 1 step 1 (one log each).
+                const double sm = h ? s[1] : s[0];
+                const int wm = h ? ex[1] : ex[0];
+                const double ym = (double)(h ? ey[1] : ey[0]);
+                const double v = fma(ym, log(sm), -sm);
+                if (wm >= 0) llh += v;
             }
             cur = nxt;
             nxt = nxt2;
