@@ -53,10 +53,11 @@ constexpr double TINY_NORMALIZER = 1e-280;   // below this the factored softmax 
 // ------------------------------------------------------- device helpers ----
 #define SCHPF_EULER 0.57721566490153286061
 
-// digamma for x > 0: upward recurrence to x >= 10, then the Bernoulli
-// asymptotic series (Abramowitz & Stegun 6.3.18); exact harmonic numbers for
-// integers <= 10.  Same arithmetic as oracle/hpf_oracle.c:oracle_psi; checked
-// against scipy.special.digamma in tests/test_gpu_kernels.py.
+// digamma for x > 0: upward recurrence to x >= 10, then the Bernoulli asymptotic series
+// (Abramowitz & Stegun 6.3.18); exact harmonic numbers for integers <= 10.  The recurrence
+// sum_j 1/(x+j) (up to 10 terms) is accumulated as ONE fraction N/D, so it costs a single
+// fp64 division instead of ten (the finalize kernels are bound by the fp64 pipe).  Checked
+// against scipy.special.digamma in tests/test_gpu_kernels.py: <= 5e-15 * max(1, |psi|).
 __device__ __forceinline__ double digamma_pos(double x)
 {
     if (!(x > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
@@ -65,11 +66,13 @@ __device__ __forceinline__ double digamma_pos(double x)
         for (int i = (int)x - 1; i >= 1; --i) y += 1.0 / (double)i;
         return y - SCHPF_EULER;
     }
-    double s = x, w = 0.0;
+    double s = x, num = 0.0, den = 1.0;
     while (s < 10.0) {
-        w += 1.0 / s;
+        num = fma(num, s, den);      // N/D + 1/s = (N s + D) / (D s)
+        den *= s;
         s += 1.0;
     }
+    const double w = num / den;
     double y = 0.0;
     if (s < 1.0e17) {
         const double z = 1.0 / (s * s);
@@ -168,6 +171,24 @@ __device__ __forceinline__ int4 ld_stream_int4(const int4 *p)
     return r;
 }
 
+__device__ __forceinline__ int2 ld_stream_int2(const int2 *p)
+{
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+// ---- entry encodings of the sweep stream ------------------------------------------
+// wide   (8 B): {row | pad<<31, count}
+// packed (4 B): pad<<31 | count<<12 | row       (count < 2^19, row < 2^12); used whenever the
+//               largest count of the matrix allows it: half the stream bytes per nonzero
+constexpr int PACKED_ROW_BITS = 12;
+constexpr int PACKED_COUNT_BITS = 19;
+__host__ __device__ inline uint32_t pack_entry(uint32_t row, uint32_t count, bool pad)
+{
+    return (pad ? 0x80000000u : 0u) | (count << PACKED_ROW_BITS) | row;
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -191,7 +212,8 @@ struct SideLayout {
     int64_t padded_entries = 0;
     int32_t *own_id = nullptr;   // [nblocks * W * 16] slot -> owner id, -1 = empty slot
     int64_t *seg_ptr = nullptr;  // [(nblocks * W) * (npanel + 1)] in step pairs
-    int4 *entries = nullptr;     // [total_pairs * 16] : {oth_local|pad, y, oth_local|pad, y}
+    void *entries = nullptr;     // [total_pairs * 16] x (int4 wide | int2 packed): two steps per element
+    bool packed = false;
     size_t bytes = 0;
     cudaStream_t stream = nullptr;   // stream the buffers were allocated on (pool_free)
     void release();
@@ -199,7 +221,7 @@ struct SideLayout {
 
 int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int32_t *d_own,
                       const int32_t *d_oth, const int32_t *d_val, int64_t n_own, int64_t n_oth,
-                      int panel_rows, int warps, int target_ctas);
+                      int panel_rows, int warps, int target_ctas, bool packed);
 
 // ------------------------------------------------------------- sweeps ------
 enum SweepMode { SWEEP_SHAPE = 0, SWEEP_LLH = 1 };
@@ -207,7 +229,7 @@ enum SweepMode { SWEEP_SHAPE = 0, SWEEP_LLH = 1 };
 struct SweepArgs {
     const int32_t *own_id;
     const int64_t *seg_ptr;
-    const int4 *entries;
+    const void *entries;     // int4 (wide) or int2 (packed) per lane pair and two steps
     const double *own_tab;   // [n_own x ST]   owner-side table (factored exp / e_x)
     const double *oth_tab;   // [npanel*Po x ST]
     double *acc;             // SHAPE: [n_own x K] sum_i w_i * oth_tab[oth_i, k]   (atomicAdd)

@@ -310,6 +310,7 @@ __global__ void validate_coo_kernel(int64_t nnz, const int32_t *__restrict__ row
     if (row[i] < 0 || row[i] >= C) f |= 1;
     if (col[i] < 0 || col[i] >= G) f |= 2;
     if (data[i] < 0) f |= 4;
+    if (data[i] >= (1 << PACKED_COUNT_BITS)) f |= 8;      // too large for the packed stream format
     if (f) atomicOr(flag, f);
 }
 

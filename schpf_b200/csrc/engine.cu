@@ -131,6 +131,7 @@ struct schpf_engine {
     int opt_target_ctas = 4736; // 148 SMs x 2 CTAs x 16 waves
     int opt_variant = 0;
     int opt_timing = 0;
+    int opt_wide_entries = 0;   // 1 = always 8-byte stream entries
     int64_t row_offset = 0;     // global index of local cell 0 (random-phi stream)
 
     bool have_coo = false, have_hyper = false, have_state = false;
@@ -403,7 +404,7 @@ int finish_coo(schpf_engine *h)
     int flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (flag) {
+    if (flag & 7) {
         set_error("COO triples out of range:%s%s%s (matrix is %lld x %lld)", (flag & 1) ? " row" : "",
                   (flag & 2) ? " col" : "", (flag & 4) ? " negative count" : "", (long long)h->C,
                   (long long)h->G);
@@ -442,11 +443,13 @@ int finish_coo(schpf_engine *h)
     int warps = sweep_default_warps(h->K);
     if (h->opt_warps > 0 && h->opt_warps < warps) warps = h->opt_warps;
     trace_mark(h->stream, "validate + tables");
+    // 4-byte entries whenever every count fits 19 bits (flag bit 8 = some count >= 2^19)
+    const bool packed = !(flag & 8) && Po <= (1 << PACKED_ROW_BITS) && !h->opt_wide_entries;
     RC_TRY(build_side_layout(h->cells, h->stream, h->nnz, h->row, h->col, h->data, h->C, h->G, Po, warps,
-                             h->opt_target_ctas));
+                             h->opt_target_ctas, packed));
     trace_mark(h->stream, "layout cells total");
     RC_TRY(build_side_layout(h->genes, h->stream, h->nnz, h->col, h->row, h->data, h->G, h->C, Po, warps,
-                             h->opt_target_ctas));
+                             h->opt_target_ctas, packed));
 
     trace_mark(h->stream, "layout genes total");
     int need = h->cells.nblocks * h->cells.nranges;
@@ -575,6 +578,7 @@ int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value)
     else if (!strcmp(key, "target_ctas")) h->opt_target_ctas = (int)value;
     else if (!strcmp(key, "variant")) h->opt_variant = (int)value;
     else if (!strcmp(key, "timing")) h->opt_timing = (int)value;
+    else if (!strcmp(key, "wide_entries")) h->opt_wide_entries = (int)value;
     else if (!strcmp(key, "row_offset")) h->row_offset = value;
     else {
         set_error("unknown option '%s'", key);
@@ -907,6 +911,7 @@ int schpf_counter(schpf_engine_t *h, const char *what, double *value)
     else if (!strcmp(what, "iterations")) *value = h->n_iterations;
     else if (!strcmp(what, "layout_bytes")) *value = (double)(h->cells.bytes + h->genes.bytes);
     else if (!strcmp(what, "panel_rows")) *value = (double)h->cells.panel_rows;
+    else if (!strcmp(what, "packed_entries")) *value = h->cells.packed ? 1.0 : 0.0;
     else if (!strcmp(what, "grid_cells")) *value = (double)h->cells.nblocks * h->cells.nranges;
     else if (!strcmp(what, "grid_genes")) *value = (double)h->genes.nblocks * h->genes.nranges;
     else if (!strcmp(what, "sweep_ms")) {

@@ -11,7 +11,8 @@
 //   the other axis is cut into panels of `panel_rows` rows;
 //   for every (warp, panel) the 16 owners' nonzeros inside that panel are
 //   stored step-interleaved (step i of all 16 pairs is contiguous), two steps
-//   per int4 {other_local | pad<<31, y, other_local | pad<<31, y};
+//   per element: int4 {other_local | pad<<31, y, other_local | pad<<31, y}, or -- when every
+//   count of the matrix is below 2^19 -- int2 of packed words pad<<31 | y<<12 | other_local;
 //   WHICH nonzero a pair handles at which step is a conflict-free schedule: a
 //   shared-memory row of the panel falls into bank group (other_local mod 4),
 //   and the four lane pairs of a quarter warp are served by one wavefront only
@@ -136,13 +137,20 @@ __global__ void warp_steps_kernel(int64_t n_warps, int npanel, const int64_t *__
     pairs[idx] = (m + 1) >> 1;
 }
 
-__global__ void fill_pad_kernel(int64_t n_int4, int4 *entries)
+template <bool PACKED>
+__global__ void fill_pad_kernel(int64_t n_elems, void *entries)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // pads read a real row of the bank group their lane pair would own in an all-pad step
     // (rows 0..3 are in groups 0..3), so they never conflict with each other
     const int o = (int)(i % GROUPS_PER_WARP) & 3;
-    if (i < n_int4) entries[i] = make_int4((int)0x80000000 | o, 0, (int)0x80000000 | o, 0);
+    if (i >= n_elems) return;
+    if (PACKED) {
+        const int w = (int)pack_entry((uint32_t)o, 0u, true);
+        reinterpret_cast<int2 *>(entries)[i] = make_int2(w, w);
+    } else {
+        reinterpret_cast<int4 *>(entries)[i] = make_int4((int)0x80000000 | o, 0, (int)0x80000000 | o, 0);
+    }
 }
 
 // the 24 permutations of {0,1,2,3}, 2 bits per element
@@ -155,9 +163,10 @@ __constant__ unsigned char PERM4[24] = {
 // remaining degree equals R must be matched (then the maximum degree drops to R-1); a
 // matching doing so always exists in a bipartite multigraph, and with 4+4 vertices the
 // 24 permutations are simply tried.
+template <bool PACKED>
 __global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__restrict__ cnt4,
                                      const int64_t *__restrict__ first4, const uint64_t *__restrict__ vals,
-                                     const int64_t *__restrict__ seg_ptr, int2 *__restrict__ entries,
+                                     const int64_t *__restrict__ seg_ptr, void *__restrict__ entries_v,
                                      int *__restrict__ unplaced)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,14 +219,20 @@ __global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__
             if (n[o][c] > 0) {
                 const int64_t src = first4[base0 + o * ostride + c] + used[o][c];
                 const uint64_t v = vals[src];
-                entries[dst] = make_int2((int)(uint32_t)v, (int)(uint32_t)(v >> 32));
+                if (PACKED)
+                    reinterpret_cast<uint32_t *>(entries_v)[dst] = pack_entry((uint32_t)v, (uint32_t)(v >> 32), false);
+                else
+                    reinterpret_cast<int2 *>(entries_v)[dst] = make_int2((int)(uint32_t)v, (int)(uint32_t)(v >> 32));
                 ++used[o][c];
                 --n[o][c];
                 --rs[o];
                 --cs[c];
             } else {
                 // idle pair: a pad that reads row c, the bank group this permutation leaves it
-                entries[dst] = make_int2((int)(0x80000000u | (unsigned)c), 0);
+                if (PACKED)
+                    reinterpret_cast<uint32_t *>(entries_v)[dst] = pack_entry((uint32_t)c, 0u, true);
+                else
+                    reinterpret_cast<int2 *>(entries_v)[dst] = make_int2((int)(0x80000000u | (unsigned)c), 0);
             }
         }
     }
@@ -254,9 +269,10 @@ void SideLayout::release()
 
 int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int32_t *d_own,
                       const int32_t *d_oth, const int32_t *d_val, int64_t n_own, int64_t n_oth,
-                      int panel_rows, int warps, int target_ctas)
+                      int panel_rows, int warps, int target_ctas, bool packed)
 {
     L.release();
+    L.packed = packed;
     if (panel_rows < 4 || panel_rows > (1 << KEY_LOCAL_BITS) || (panel_rows & 3)) {
         set_error("panel_rows must be a multiple of 4 in [4, %d], got %d", 1 << KEY_LOCAL_BITS, panel_rows);
         return SCHPF_ERR_ARG;
@@ -360,14 +376,23 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
 
     trace_mark(stream, "  scans + lengths");
     // 4. entry stream
-    const int64_t n_int4 = total_pairs * GROUPS_PER_WARP;
-    CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&L.entries), sizeof(int4) * (n_int4 > 0 ? n_int4 : 1), stream));
-    if (n_int4 > 0) fill_pad_kernel<<<blocks_for(n_int4, 256), 256, 0, stream>>>(n_int4, L.entries);
+    const int64_t n_elems = total_pairs * GROUPS_PER_WARP;      // one element = two steps of a lane pair
+    const size_t elem_bytes = packed ? sizeof(int2) : sizeof(int4);
+    CUDA_TRY(pool_malloc(&L.entries, elem_bytes * (n_elems > 0 ? n_elems : 1), stream));
+    if (n_elems > 0) {
+        if (packed) fill_pad_kernel<true><<<blocks_for(n_elems, 256), 256, 0, stream>>>(n_elems, L.entries);
+        else fill_pad_kernel<false><<<blocks_for(n_elems, 256), 256, 0, stream>>>(n_elems, L.entries);
+    }
     if (nnz > 0) {
         const int64_t n_qw = n_slots / 4;
-        place_entries_kernel<<<blocks_for(n_qw * L.npanel, 128), 128, 0, stream>>>(
-            n_qw, L.npanel, seg_cnt.as<int64_t>(), seg_first.as<int64_t>(), vals2.as<uint64_t>(), L.seg_ptr,
-            reinterpret_cast<int2 *>(L.entries), unplaced.as<int>());
+        if (packed)
+            place_entries_kernel<true><<<blocks_for(n_qw * L.npanel, 128), 128, 0, stream>>>(
+                n_qw, L.npanel, seg_cnt.as<int64_t>(), seg_first.as<int64_t>(), vals2.as<uint64_t>(), L.seg_ptr,
+                L.entries, unplaced.as<int>());
+        else
+            place_entries_kernel<false><<<blocks_for(n_qw * L.npanel, 128), 128, 0, stream>>>(
+                n_qw, L.npanel, seg_cnt.as<int64_t>(), seg_first.as<int64_t>(), vals2.as<uint64_t>(), L.seg_ptr,
+                L.entries, unplaced.as<int>());
     }
     CUDA_TRY(cudaGetLastError());
     trace_mark(stream, "  schedule + place");
@@ -379,7 +404,7 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
         L.release();
         return SCHPF_ERR_STATE;
     }
-    L.bytes = sizeof(int32_t) * n_slots + sizeof(int64_t) * n_ptr + sizeof(int4) * n_int4;
+    L.bytes = sizeof(int32_t) * n_slots + sizeof(int64_t) * n_ptr + elem_bytes * n_elems;
     return SCHPF_OK;
 }
 

@@ -66,10 +66,39 @@ struct SweepCfg {
     static constexpr int MAX_WARPS = sweep_max_warps(KP);
 };
 
-template <int KP, int MODE>
+// two steps of a lane pair as fetched from the entry stream, and their decoded form
+template <bool PACKED> struct EntryPair;
+template <> struct EntryPair<false> {
+    int4 v;
+    __device__ __forceinline__ static EntryPair zero() { return {make_int4(0, 0, 0, 0)}; }
+    __device__ __forceinline__ static EntryPair load(const void *base, int64_t idx)
+    {
+        return {ld_stream_int4(reinterpret_cast<const int4 *>(base) + idx)};
+    }
+    __device__ __forceinline__ int row(int e) const { return (e ? v.z : v.x) & 0x7fffffff; }
+    __device__ __forceinline__ int count(int e) const { return e ? v.w : v.y; }
+    __device__ __forceinline__ bool pad(int e) const { return (e ? v.z : v.x) < 0; }
+};
+template <> struct EntryPair<true> {
+    int2 v;
+    __device__ __forceinline__ static EntryPair zero() { return {make_int2(0, 0)}; }
+    __device__ __forceinline__ static EntryPair load(const void *base, int64_t idx)
+    {
+        return {ld_stream_int2(reinterpret_cast<const int2 *>(base) + idx)};
+    }
+    __device__ __forceinline__ int row(int e) const { return (e ? v.y : v.x) & ((1 << PACKED_ROW_BITS) - 1); }
+    __device__ __forceinline__ int count(int e) const
+    {
+        return ((e ? v.y : v.x) >> PACKED_ROW_BITS) & ((1 << PACKED_COUNT_BITS) - 1);
+    }
+    __device__ __forceinline__ bool pad(int e) const { return (e ? v.y : v.x) < 0; }
+};
+
+template <int KP, int MODE, bool PACKED>
 __global__ void __launch_bounds__(SweepCfg<KP>::MAX_WARPS * 32, SweepCfg<KP>::MIN_CTAS)
 sweep_kernel(const SweepArgs A)
 {
+    using Ent = EntryPair<PACKED>;
     using Cfg = SweepCfg<KP>;
     constexpr int ST = Cfg::ST, U = Cfg::U, D = Cfg::D;
 
@@ -117,14 +146,14 @@ sweep_kernel(const SweepArgs A)
 
     // this warp's first panel: segment bounds and the first two entry pairs
     int64_t i0 = 0, i1 = 0;
-    int4 cur = make_int4(0, 0, 0, 0), nxt = cur;
-    const int4 *ep = A.entries;
+    Ent cur = Ent::zero(), nxt = cur;
+    int64_t ep = 0;                     // element index of this lane pair's current int4 / int2
     if (p0 < p1) {
         i0 = sp[p0];
         i1 = sp[p0 + 1];
-        ep = A.entries + i0 * GROUPS_PER_WARP + q;
-        if (i0 < i1) cur = ld_stream_int4(ep);
-        if (i0 + 1 < i1) nxt = ld_stream_int4(ep + GROUPS_PER_WARP);
+        ep = i0 * GROUPS_PER_WARP + q;
+        if (i0 < i1) cur = Ent::load(A.entries, ep);
+        if (i0 + 1 < i1) nxt = Ent::load(A.entries, ep + GROUPS_PER_WARP);
     }
 
     for (int p = p0; p < p1; ++p) {
@@ -144,9 +173,10 @@ sweep_kernel(const SweepArgs A)
 
         for (int64_t i = i0; i < i1; ++i) {
             ep += GROUPS_PER_WARP;
-            int4 nxt2 = nxt;
-            if (i + 2 < i1) nxt2 = ld_stream_int4(ep + GROUPS_PER_WARP);
-            const int ex[2] = {cur.x, cur.z}, ey[2] = {cur.y, cur.w};
+            Ent nxt2 = nxt;
+            if (i + 2 < i1) nxt2 = Ent::load(A.entries, ep + GROUPS_PER_WARP);
+            const int ex[2] = {cur.row(0), cur.row(1)}, ey[2] = {cur.count(0), cur.count(1)};
+            const bool epad[2] = {cur.pad(0), cur.pad(1)};
             double s[2];
             bool slow = false;
 #if SWEEP_INTERLEAVE
@@ -158,7 +188,7 @@ sweep_kernel(const SweepArgs A)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 // pad entries (bit 31, count 0) point at a row of a free bank group
-                const uint32_t addr = panel_s + (uint32_t)(ex[e] & 0x7fffffff) * (ST * 8) + h * 16;
+                const uint32_t addr = panel_s + (uint32_t)ex[e] * (ST * 8) + h * 16;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
 #if SWEEP_PAD_PRED
@@ -201,7 +231,7 @@ sweep_kernel(const SweepArgs A)
 #else
                 double b1[D];
 #endif
-                const uint32_t addr = panel_s + (uint32_t)(ex[e] & 0x7fffffff) * (ST * 8) + h * 16;
+                const uint32_t addr = panel_s + (uint32_t)ex[e] * (ST * 8) + h * 16;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
 #if SWEEP_PAD_PRED
@@ -240,7 +270,7 @@ sweep_kernel(const SweepArgs A)
                         if (s[e] > TINY_NORMALIZER || ey[e] == 0) continue;
                         const double y = (double)ey[e];
                         const double *eo = A.own_elog + (int64_t)own * K;
-                        const double *et = A.oth_elog + ((int64_t)p * A.panel_rows + (ex[e] & 0x7fffffff)) * K;
+                        const double *et = A.oth_elog + ((int64_t)p * A.panel_rows + ex[e]) * K;
                         double largest = -INFINITY, normalizer = 0.0;
 #pragma unroll 1
                         for (int k = 0; k < K; ++k) largest = fmax(largest, eo[k] + et[k]);
@@ -261,10 +291,10 @@ sweep_kernel(const SweepArgs A)
                 // hpf_numba.py:49-50 without the lgamma term (a constant of the data).  Both lanes of
                 // a pair hold both normalisers: lane 0 finishes step 0, lane 1 step 1 (one log each).
                 const double sm = h ? s[1] : s[0];
-                const int wm = h ? ex[1] : ex[0];
+                const bool padm = h ? epad[1] : epad[0];
                 const double ym = (double)(h ? ey[1] : ey[0]);
                 const double v = fma(ym, log(sm), -sm);
-                if (wm >= 0) llh += v;
+                if (!padm) llh += v;
             }
             cur = nxt;
             nxt = nxt2;
@@ -272,9 +302,9 @@ sweep_kernel(const SweepArgs A)
         // first entries of the next panel: issued before the barrier so their latency overlaps it
         i0 = n0;
         i1 = n1;
-        ep = A.entries + i0 * GROUPS_PER_WARP + q;
-        if (i0 < i1) cur = ld_stream_int4(ep);
-        if (i0 + 1 < i1) nxt = ld_stream_int4(ep + GROUPS_PER_WARP);
+        ep = i0 * GROUPS_PER_WARP + q;
+        if (i0 < i1) cur = Ent::load(A.entries, ep);
+        if (i0 + 1 < i1) nxt = Ent::load(A.entries, ep + GROUPS_PER_WARP);
     }
 
     if (MODE == SWEEP_SHAPE) {
@@ -301,23 +331,23 @@ sweep_kernel(const SweepArgs A)
     }
 }
 
-template <int KP, int MODE>
-int launch_one(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
+template <int KP, int MODE, bool PACKED>
+int launch_packed(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
 {
     const size_t smem = (size_t)L.panel_rows * SweepCfg<KP>::ST * 8 + 16;
     static bool configured = false;   // per instantiation
     static size_t configured_smem = 0;
     if (!configured || smem > configured_smem) {
-        CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<KP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<KP, MODE, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<KP, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<KP, MODE, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
         configured = true;
         configured_smem = smem;
     }
     const int grid = L.nblocks * L.nranges;
     if (grid <= 0) return SCHPF_OK;
-    sweep_kernel<KP, MODE><<<grid, L.warps * 32, smem, stream>>>(args);
+    sweep_kernel<KP, MODE, PACKED><<<grid, L.warps * 32, smem, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("sweep_kernel<KP=%d,mode=%d> launch (grid %d, block %d, smem %zu) -> %s", KP, MODE, grid,
@@ -325,6 +355,12 @@ int launch_one(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
         return SCHPF_ERR_CUDA;
     }
     return SCHPF_OK;
+}
+
+template <int KP, int MODE>
+int launch_one(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
+{
+    return L.packed ? launch_packed<KP, MODE, true>(L, args, stream) : launch_packed<KP, MODE, false>(L, args, stream);
 }
 
 template <int MODE>

@@ -403,3 +403,32 @@ def test_run_trials_on_device(g_reinit, g_project, capsys):
     np.random.seed(5)
     pool = run_trials_pool(X, [2, 3], ntrials=2, min_iter=3, max_iter=3, check_freq=1)
     assert [p.nfactors for p in pool] == [2, 3] and all(np.isfinite(p.loss[-1]) for p in pool)
+
+
+def test_packed_and_wide_entry_streams_agree():
+    """The 4-byte stream format (row | count<<12 | pad<<31) is used whenever all counts are
+    below 2^19; the 8-byte format otherwise.  Same numbers either way; a single large count
+    switches the format automatically."""
+    row, col, data, st = _random_problem(350, 500, 20, 25000, 17)
+    big = data.copy()
+    big[7] = (1 << 19) + 5                      # does not fit the packed format
+    results = {}
+    for name, d, opts in (("packed", data, {}), ("wide", data, {"wide_entries": 1}), ("auto_wide", big, {})):
+        with CaviEngine(350, 500, 20, **opts) as e:
+            e.set_coo(row, col, d)
+            e.set_hyper(0.3, 1.0, 0.7, 0.3, 1.0, 1.3)
+            e.set_state(theta=(st.theta_shp, st.theta_rte), beta=(st.beta_shp, st.beta_rte),
+                        xi=(st.xi_shp, st.xi_rte), eta=(st.eta_shp, st.eta_rte))
+            e.step(4)
+            results[name] = (e.get_state(), e.loss(), e.counter("packed_entries"), e.llh_pointwise())
+    assert results["packed"][2] == 1 and results["wide"][2] == 0 and results["auto_wide"][2] == 0
+    for n in NAMES:
+        assert max_rel(results["packed"][0][n][0], results["wide"][0][n][0]) < 1e-12
+        assert max_rel(results["packed"][0][n][1], results["wide"][0][n][1]) < 1e-12
+    assert_allclose(results["packed"][1], results["wide"][1], rtol=1e-13)
+    # the large count is honoured: oracle on the modified data
+    st2 = st.copy()
+    oc.cavi_run(big, row, col, st2, 0.3, 1.0, 0.7, 0.3, 1.0, 1.3, 4)
+    assert max_rel(results["auto_wide"][0]["theta"][0], st2.theta_shp) < TOL
+    assert max_rel(results["auto_wide"][0]["beta"][0], st2.beta_shp) < TOL
+    assert_allclose(results["auto_wide"][1], np.mean(-results["auto_wide"][3]), rtol=1e-12)

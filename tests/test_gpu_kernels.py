@@ -30,9 +30,9 @@ def test_digamma_dense_grid():
     x = np.exp(np.linspace(np.log(1e-4), np.log(1e6), 200001))
     got, want = hpf_cuda.psi(x), digamma(x)
     err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
-    assert err.max() < 4e-15
-    # device and C oracle run the same arithmetic (FMA contraction aside)
-    assert np.abs(got - oc.psi(x)).max() / 1.0 < 1e-11
+    assert err.max() < 5e-15
+    # device and C oracle: same series, the device sums its recurrence as one fraction
+    assert (np.abs(got - oc.psi(x)) / np.maximum(1.0, np.abs(want))).max() < 1e-14
     # Gauss special values (scipy/special/tests/test_digamma.py)
     eg = np.euler_gamma
     vals = hpf_cuda.psi(np.array([1.0, 0.5, 1 / 3., 0.25]))
