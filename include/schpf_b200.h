@@ -107,7 +107,8 @@ int schpf_destroy(schpf_engine_t *h);
 /* tuning knobs, before schpf_set_coo: "panel_rows", "warps_per_cta",
  * "target_ctas", "variant" (0 = tiled two-pass sweep, 1 = literal per-nnz
  * kernel with atomics), "timing" (1 = record CUDA events around the sweeps),
- * "wide_entries" (1 = 8-byte stream entries even when all counts fit the 4-byte format) */
+ * "packed_entries" (1 = 4-byte stream entries when every count is < 2^19: half the
+ * resident layout, slightly slower sweeps) */
 int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value);
 
 /* The sparse count matrix as COO triples (X.row, X.col, X.data of a

@@ -131,7 +131,7 @@ struct schpf_engine {
     int opt_target_ctas = 4736; // 148 SMs x 2 CTAs x 16 waves
     int opt_variant = 0;
     int opt_timing = 0;
-    int opt_wide_entries = 0;   // 1 = always 8-byte stream entries
+    int opt_packed_entries = 0; // 1 = 4-byte stream entries when every count is < 2^19
     int64_t row_offset = 0;     // global index of local cell 0 (random-phi stream)
 
     bool have_coo = false, have_hyper = false, have_state = false;
@@ -443,8 +443,11 @@ int finish_coo(schpf_engine *h)
     int warps = sweep_default_warps(h->K);
     if (h->opt_warps > 0 && h->opt_warps < warps) warps = h->opt_warps;
     trace_mark(h->stream, "validate + tables");
-    // 4-byte entries whenever every count fits 19 bits (flag bit 8 = some count >= 2^19)
-    const bool packed = !(flag & 8) && Po <= (1 << PACKED_ROW_BITS) && !h->opt_wide_entries;
+    // 4-byte entries are possible when every count fits 19 bits (flag bit 8 = some count >= 2^19).
+    // Measured on cfg-3 they are SLOWER than 8-byte entries (3.61 vs 3.43 ms per sweep pair: the
+    // sweep is not HBM-bound and the decode costs issue slots), so they are opt-in: they halve
+    // the resident layout (1.8 GB instead of 3.6 GB at 1.9e8 nnz) when memory matters.
+    const bool packed = h->opt_packed_entries && !(flag & 8) && Po <= (1 << PACKED_ROW_BITS);
     RC_TRY(build_side_layout(h->cells, h->stream, h->nnz, h->row, h->col, h->data, h->C, h->G, Po, warps,
                              h->opt_target_ctas, packed));
     trace_mark(h->stream, "layout cells total");
@@ -578,7 +581,7 @@ int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value)
     else if (!strcmp(key, "target_ctas")) h->opt_target_ctas = (int)value;
     else if (!strcmp(key, "variant")) h->opt_variant = (int)value;
     else if (!strcmp(key, "timing")) h->opt_timing = (int)value;
-    else if (!strcmp(key, "wide_entries")) h->opt_wide_entries = (int)value;
+    else if (!strcmp(key, "packed_entries")) h->opt_packed_entries = (int)value;
     else if (!strcmp(key, "row_offset")) h->row_offset = value;
     else {
         set_error("unknown option '%s'", key);

@@ -406,14 +406,14 @@ def test_run_trials_on_device(g_reinit, g_project, capsys):
 
 
 def test_packed_and_wide_entry_streams_agree():
-    """The 4-byte stream format (row | count<<12 | pad<<31) is used whenever all counts are
-    below 2^19; the 8-byte format otherwise.  Same numbers either way; a single large count
-    switches the format automatically."""
+    """The opt-in 4-byte stream format (row | count<<12 | pad<<31) needs all counts below 2^19;
+    otherwise the 8-byte format is kept.  Same numbers either way."""
     row, col, data, st = _random_problem(350, 500, 20, 25000, 17)
     big = data.copy()
     big[7] = (1 << 19) + 5                      # does not fit the packed format
     results = {}
-    for name, d, opts in (("packed", data, {}), ("wide", data, {"wide_entries": 1}), ("auto_wide", big, {})):
+    for name, d, opts in (("packed", data, {"packed_entries": 1}), ("wide", data, {}),
+                          ("auto_wide", big, {"packed_entries": 1})):
         with CaviEngine(350, 500, 20, **opts) as e:
             e.set_coo(row, col, d)
             e.set_hyper(0.3, 1.0, 0.7, 0.3, 1.0, 1.3)
