@@ -29,6 +29,55 @@ _engine_factory = None
 HOST_DIRICHLET_LIMIT = 1 << 24
 
 
+# ---- helpers for cell-sharded fits (torch.distributed; any backend) ----------------
+def _dist_device(group):
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def _global_mean_var_ratio(group, local_sums, sharded_axis):
+    """mean / population variance of the totals along one axis of the sharded matrix.
+    Cell totals (sharded axis) are pooled as moments, gene totals are summed over ranks."""
+    import torch
+    import torch.distributed as dist
+    dev = _dist_device(group)
+    if sharded_axis:
+        m = torch.tensor([local_sums.sum(), (local_sums ** 2).sum(), float(local_sums.shape[0])],
+                         dtype=torch.float64, device=dev)
+        dist.all_reduce(m, group=group)
+        s1, s2, n = m.tolist()
+        mean = s1 / n
+        return mean / (s2 / n - mean * mean)
+    t = torch.as_tensor(local_sums, dtype=torch.float64).to(dev)
+    dist.all_reduce(t, group=group)
+    tot = t.cpu().numpy()
+    return np.mean(tot) / np.var(tot)
+
+
+def _replicate_from_rank0(group, *gammas):
+    """Every rank gets rank 0's copies (the gene side must be identical everywhere)."""
+    import torch
+    import torch.distributed as dist
+    dev, src, out = _dist_device(group), (dist.get_global_rank(group, 0) if group is not None else 0), []
+    for g in gammas:
+        pair = []
+        for arr in (g.vi_shape, g.vi_rate):
+            t = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(dev)
+            dist.broadcast(t, src=src, group=group)
+            pair.append(t.cpu().numpy().astype(arr.dtype, copy=False))
+        out.append(HPF_Gamma(*pair))
+    return out
+
+
+def _shared_seed(group):
+    """One random-phi seed for all ranks, drawn from rank 0's numpy stream."""
+    import torch.distributed as dist
+    box = [int(np.random.randint(0, 2 ** 31 - 1))]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return box[0]
+
+
 class HPF_Gamma(object):
     """A family of independent Gamma(vi_shape, vi_rate) variational distributions
     (reference: scHPF_.py:27-178)."""
@@ -248,10 +297,16 @@ class scHPF(BaseEstimator):
     def _fit(self, X, freeze_genes=False, reinit=True, loss_function=None,
              min_iter=None, max_iter=None, epsilon=None, check_freq=None,
              single_process=False, checkstep_function=None, verbose=None,
-             batchsize=None, beta_theta_simultaneous=False, loss_smoothing=1):
+             batchsize=None, beta_theta_simultaneous=False, loss_smoothing=1,
+             process_group=None):
         """Host driver of the device CAVI loop; arguments and return value as
         scHPF_.py:526-604.  `single_process` is accepted and ignored (there is
-        one device path)."""
+        one device path).
+
+        `process_group` (the only addition): a torch.distributed group whose ranks each pass
+        their own contiguous shard of the cells as `X` (all genes).  b', d' come from the whole
+        matrix, eta/beta are rank 0's draws on every rank, the loss is the loss over all
+        cells, and the returned xi/theta are this rank's rows."""
         assert loss_smoothing > 0
         nfactors, (ncells, ngenes) = self.nfactors, X.shape
         a, ap, c, cp = self.a, self.ap, self.c, self.cp
@@ -260,7 +315,7 @@ class scHPF(BaseEstimator):
                 'minibatch CAVI (batchsize) is not part of the device loop yet; '
                 'use batchsize=None (DESIGN.md, out of scope)')
 
-        bp, dp, xi, eta, theta, beta = self._setup(X, freeze_genes, reinit)
+        bp, dp, xi, eta, theta, beta = self._setup(X, freeze_genes, reinit, process_group=process_group)
         # capacity shapes are constants of the fit (scHPF_.py:614-618)
         xi.vi_shape[:] = ap + nfactors * a
         if not freeze_genes:
@@ -273,6 +328,9 @@ class scHPF(BaseEstimator):
         verbose = self.verbose if verbose is None else verbose
 
         engine = self._new_engine(ncells, ngenes)
+        if process_group is not None:
+            from .engine import ShardedEngine
+            engine = ShardedEngine(engine, process_group)
         try:
             engine.set_coo(X.row, X.col, X.data)
             engine.set_hyper(a, ap, bp, c, cp, dp)
@@ -298,7 +356,10 @@ class scHPF(BaseEstimator):
                 if t == 0 and reinit:
                     # first iteration from a random phi instead of the E-step (:652-655)
                     nnz = X.data.shape[0]
-                    if nnz * nfactors <= HOST_DIRICHLET_LIMIT:
+                    if process_group is not None:
+                        engine.step(1, freeze_genes=freeze_genes, simultaneous=beta_theta_simultaneous,
+                                    random_phi_seed=_shared_seed(process_group))
+                    elif nnz * nfactors <= HOST_DIRICHLET_LIMIT:
                         random_phi = np.random.dirichlet(np.ones(nfactors), nnz)
                         engine.step_with_xphi(X.data[:, None] * random_phi, freeze_genes=freeze_genes,
                                               simultaneous=beta_theta_simultaneous)
@@ -360,14 +421,14 @@ class scHPF(BaseEstimator):
         return (bp, dp, xi, eta, theta, beta, loss)
 
     # ---- setup (host, bit-identical to the reference) ------------------------
-    def _setup(self, X, freeze_genes=False, reinit=True, clip=True):
+    def _setup(self, X, freeze_genes=False, reinit=True, clip=True, process_group=None):
         """Empirical b', d' and (re)initialised distributions, drawing from the
         numpy global RNG in the reference's order xi, theta, eta, beta
         (scHPF_.py:783-844)."""
         nfactors, (ncells, ngenes) = self.nfactors, X.shape
         a, ap, c, cp = self.a, self.ap, self.c, self.cp
         xi, eta, theta, beta = self.xi, self.eta, self.theta, self.beta
-        bp, dp = self._get_empirical_hypers(X, freeze_genes, clip)
+        bp, dp = self._get_empirical_hypers(X, freeze_genes, clip, process_group=process_group)
         make = HPF_Gamma.random_gamma_factory
         if reinit or xi is None:
             xi = make((ncells,), ap, bp, dtype=self.dtype)
@@ -383,15 +444,21 @@ class scHPF(BaseEstimator):
                 eta = make((ngenes,), cp, dp, dtype=self.dtype)
             if reinit or beta is None:
                 beta = make((ngenes, nfactors), c, dp, dtype=self.dtype)
+            if process_group is not None:
+                eta, beta = _replicate_from_rank0(process_group, eta, beta)
         return (bp, dp, xi, eta, theta, beta)
 
-    def _get_empirical_hypers(self, X, freeze_genes=False, clip=True):
+    def _get_empirical_hypers(self, X, freeze_genes=False, clip=True, process_group=None):
         """b' = a' * mean/var of the cell totals, d' = c' * mean/var of the gene
-        totals (population variance), d' clipped to b'/1000 (scHPF_.py:847-879)."""
+        totals (population variance), d' clipped to b'/1000 (scHPF_.py:847-879).
+        With a process group the totals are those of the whole (sharded) matrix."""
         bp, dp = self.bp, self.dp
 
         def mean_var_ratio(axis):
             axis_sum = X.sum(axis=axis)
+            if process_group is not None:
+                return _global_mean_var_ratio(process_group, np.asarray(axis_sum, dtype=np.float64).ravel(),
+                                              sharded_axis=(axis == 1))
             return np.mean(axis_sum) / np.var(axis_sum)
         if bp is None:
             bp = self.ap * mean_var_ratio(1)

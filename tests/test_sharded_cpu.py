@@ -88,3 +88,54 @@ def test_two_rank_gloo_matches_unsharded(tmp_path, freeze):
         onp.cavi_run(g["data"], g["row"], g["col"], st, *hyp, 10, freeze_genes=True)
         assert rel(np.concatenate([r[0]["theta_shp"], r[1]["theta_shp"]]), st.theta_shp) < 1e-12
         assert rel(np.concatenate([r[0]["xi_rte"], r[1]["xi_rte"]]), st.xi_rte) < 1e-12
+
+
+def _estimator_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from scipy.sparse import coo_matrix
+    from schpf_b200 import scHPF, HPF_Gamma
+    from schpf_b200 import scHPF_ as shell
+    from schpf_b200.engine import shard_bounds_by_nnz
+    from oracle_engine import OracleEngine
+    shell._engine_factory = OracleEngine               # host logic under test, arithmetic from the oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = dict(np.load(os.path.join(GOLDEN, "cavi_cfg1.npz")))
+    C, G = (int(v) for v in g["shape"])
+    b = shard_bounds_by_nnz(np.bincount(g["row"], minlength=C), world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    keep = (g["row"] >= lo) & (g["row"] < hi)
+    X = coo_matrix((g["data"][keep], (g["row"][keep] - lo, g["col"][keep])), shape=(hi - lo, G))
+    gam = lambda n, sl: HPF_Gamma(g["init_" + n + "_shp"][sl].copy(), g["init_" + n + "_rte"][sl].copy())
+    # rank 1 is handed garbage for the gene side: it must end up with rank 0's
+    scale = 1.0 if rank == 0 else 3.0
+    beta = HPF_Gamma(g["init_beta_shp"] * scale, g["init_beta_rte"] * scale)
+    eta = HPF_Gamma(g["init_eta_shp"] * scale, g["init_eta_rte"] * scale)
+    m = scHPF(5, verbose=False, xi=gam("xi", slice(lo, hi)), theta=gam("theta", slice(lo, hi)), eta=eta, beta=beta)
+    m.fit(X, reinit=False, min_iter=10, max_iter=10, check_freq=3, process_group=dist.group.WORLD)
+    np.savez(os.path.join(out_dir, "est%d.npz" % rank), lo=lo, hi=hi, bp=m.bp, dp=m.dp, loss=np.array(m.loss),
+             theta_shp=m.theta.vi_shape, xi_rte=m.xi.vi_rate, beta_shp=m.beta.vi_shape, eta_rte=m.eta.vi_rate)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_estimator_fit_with_process_group(tmp_path):
+    """scHPF.fit(X_shard, process_group=...) on two gloo ranks: global b', d', gene side taken
+    from rank 0, global loss, and the same result as the reference's unsharded run."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_estimator_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = dict(np.load(os.path.join(GOLDEN, "cavi_cfg1.npz")))
+    r = [dict(np.load(str(tmp_path / ("est%d.npz" % k)))) for k in range(world)]
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.abs(b)))
+    for k in range(world):
+        assert abs(float(r[k]["bp"]) / float(g["bp"]) - 1) < 1e-12       # pooled moments, not np.var: ~1 ulp
+        assert abs(float(r[k]["dp"]) / float(g["dp"]) - 1) < 1e-12
+    assert np.array_equal(r[0]["beta_shp"], r[1]["beta_shp"]) and np.array_equal(r[0]["loss"], r[1]["loss"])
+    assert rel(r[0]["beta_shp"], g["it10_beta_shp"]) < 1e-10
+    assert rel(np.concatenate([r[0]["theta_shp"], r[1]["theta_shp"]]), g["it10_theta_shp"]) < 1e-10
+    assert rel(np.concatenate([r[0]["xi_rte"], r[1]["xi_rte"]]), g["it10_xi_rte"]) < 1e-10
+    assert np.allclose(r[0]["loss"], g["it10_loss"], rtol=1e-10)
