@@ -44,6 +44,10 @@ extern "C" {
 /* flags for schpf_step* */
 #define SCHPF_FREEZE_GENES  1   /* skip every beta/eta update (scHPF_.py:617,668,682,697) */
 #define SCHPF_SIMULTANEOUS  2   /* beta_theta_simultaneous=True ordering (scHPF_.py:666-684) */
+#define SCHPF_CELLS_FIRST   4   /* minibatch ordering (scHPF_.py:686-704, `batched`): theta/xi are updated
+                                   first (from the old beta), and beta's rate then sees the NEW theta.
+                                   Single engine only: with an attached communicator the exchange
+                                   buffer already holds the old theta's column sums -> SCHPF_ERR_ARG. */
 
 typedef struct schpf_engine schpf_engine_t;
 
@@ -135,6 +139,11 @@ int schpf_get_state(schpf_engine_t *h,
                     double *beta_shp, double *beta_rte,
                     double *xi_shp, double *xi_rte,
                     double *eta_shp, double *eta_rte);
+
+/* Copy beta and eta (shape and rate) from `src` to `dst`, device to device.  Both handles must be on
+ * the same device with the same ngenes / nfactors.  This is how the minibatch loop (scHPF_.py:642-650:
+ * a different row subset of X every iteration) hands the gene side from one batch's engine to the next. */
+int schpf_copy_gene_state(schpf_engine_t *dst, schpf_engine_t *src);
 
 /* n full CAVI iterations (Xphi -> beta -> eta -> theta -> xi), single GPU. */
 int schpf_step(schpf_engine_t *h, int n_iters, int flags);

@@ -19,7 +19,7 @@ Reference lines followed (all paths relative to the reference checkout):
   schpf/hpf_numba.py:160-177  compute_loading_rate_update
   schpf/hpf_numba.py:181-188  compute_capacity_rate_update
   schpf/loss.py:107-168       pois_llh_pointwise / mean_negative_pois_llh
-  schpf/scHPF_.py:605-780     _fit iteration order and convergence logic
+  schpf/scHPF_.py:605-780     _fit iteration order (full batch, simultaneous, minibatch)
   schpf/scHPF_.py:847-879     _get_empirical_hypers
 """
 import numpy as np
@@ -149,8 +149,9 @@ def cavi_prepare(st, a, ap, c, cp, nfactors, freeze_genes=False):
 
 
 def cavi_iteration(X_data, X_row, X_col, st, a, bp, c, dp, freeze_genes=False,
-                   Xphi=None, beta_theta_simultaneous=False):
-    """One pass of the loop body, scHPF_.py:661-714, non-batched.
+                   Xphi=None, beta_theta_simultaneous=False, batched=False):
+    """One pass of the loop body, scHPF_.py:661-714, over the cells in ``st``
+    (all cells, or -- ``batched`` -- the rows of one minibatch re-based to 0..).
 
     ``Xphi`` may be supplied (the t==0 random-phi branch, :652-655).
     Default ordering: beta -> eta -> theta -> xi (the ``not batched`` branch);
@@ -174,11 +175,20 @@ def cavi_iteration(X_data, X_row, X_col, st, a, bp, c, dp, freeze_genes=False,
             st.beta_shp, st.beta_rte = bvs, bvr
             st.eta_rte = dp + (st.beta_shp / st.beta_rte).sum(1)
         return st
+    if batched:
+        # scHPF_.py:686-694: "cell updates, must do first for batching" -- beta's rate below
+        # then sees the NEW theta of the batch (:697-704)
+        st.theta_shp = compute_loading_shape_update(Xphi, X_row, ncells, a)
+        st.theta_rte = compute_loading_rate_update(st.xi_shp, st.xi_rte,
+                                                   st.beta_shp, st.beta_rte)
+        st.xi_rte = bp + (st.theta_shp / st.theta_rte).sum(1)
     if not freeze_genes:
         st.beta_shp = compute_loading_shape_update(Xphi, X_col, ngenes, c)
         st.beta_rte = compute_loading_rate_update(st.eta_shp, st.eta_rte,
                                                   st.theta_shp, st.theta_rte)
         st.eta_rte = dp + (st.beta_shp / st.beta_rte).sum(1)
+    if batched:
+        return st
     st.theta_shp = compute_loading_shape_update(Xphi, X_row, ncells, a)
     st.theta_rte = compute_loading_rate_update(st.xi_shp, st.xi_rte,
                                                st.beta_shp, st.beta_rte)

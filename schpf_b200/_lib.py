@@ -42,6 +42,7 @@ SIGNATURES = {
     "schpf_set_hyper": [c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl],
     "schpf_set_state": [c_vp] + [c_vp] * 8,
     "schpf_get_state": [c_vp] + [c_vp] * 8,
+    "schpf_copy_gene_state": [c_vp, c_vp],
     "schpf_step": [c_vp, c_int, c_int],
     "schpf_step_with_xphi": [c_vp, p_dbl, c_int],
     "schpf_step_random_phi": [c_vp, c_u64, c_int],
@@ -62,6 +63,7 @@ SIGNATURES = {
 
 FREEZE_GENES = 1
 SIMULTANEOUS = 2
+CELLS_FIRST = 4
 MAX_FACTORS = 64
 
 _lib = None

@@ -1,0 +1,195 @@
+"""Device-side drivers of the iteration body of the reference's `_fit`
+(schpf/scHPF_.py:642-715).  `scHPF._fit` keeps the scalar bookkeeping (loss list,
+percent change, stopping rules) and asks one of these for iterations, the loss and
+the host copy of the state:
+
+  FullBatchLoop   every iteration sees all cells (the default, `batched == False`)
+  MinibatchLoop   `batchsize` cells per iteration (scHPF_.py:626-631, 642-650, 686-704)
+
+Both talk to the GPU only through `engine.CaviEngine` (the C ABI).
+"""
+from math import gcd
+
+import numpy as np
+
+# nnz * K above which the t == 0 random-phi draw moves from numpy (bit-compatible
+# with a seeded reference run, scHPF_.py:652-655) to the device generator
+HOST_DIRICHLET_LIMIT = 1 << 24
+
+# a minibatch window gets an engine (= its own device layout) of its own while the number of
+# distinct windows is at most this; beyond, one engine is re-laid out every iteration
+MINIBATCH_ENGINE_CACHE = 64
+
+
+def minibatch_windows(ncells, batchsize):
+    """The reference's batch schedule (schpf/util.py:218-231): ONE `np.random.shuffle` of the
+    cell order at the first draw, then consecutive windows of `batchsize` cells that wrap
+    around the end.  Yields (window start, cell indices)."""
+    assert ncells >= batchsize
+    order = np.arange(ncells)
+    np.random.shuffle(order)
+    offsets = np.arange(batchsize)
+    start = 0
+    while True:
+        yield start, order[(start + offsets) % ncells]
+        start = (start + batchsize) % ncells
+
+
+def _random_phi_step(engine, data, nfactors, **flags):
+    """First iteration from y * Dirichlet(1_K) instead of the E-step (scHPF_.py:652-655):
+    numpy's stream while the draw is small enough to make on the host, the device's
+    counter-based generator (seeded from numpy's stream) beyond."""
+    nnz = data.shape[0]
+    if nnz * nfactors <= HOST_DIRICHLET_LIMIT:
+        random_phi = np.random.dirichlet(np.ones(nfactors), nnz)
+        engine.step_with_xphi(data[:, None] * random_phi, **flags)
+    else:
+        engine.step_random_phi(int(np.random.randint(0, 2 ** 31 - 1)), **flags)
+
+
+class FullBatchLoop(object):
+    """All cells every iteration; with `process_group`, this rank's shard of the cells."""
+
+    def __init__(self, new_engine, X, hyper, state, nfactors, freeze_genes, simultaneous,
+                 process_group=None, shared_seed=None):
+        self.X, self.nfactors = X, nfactors
+        self.flags = dict(freeze_genes=freeze_genes, simultaneous=simultaneous)
+        self.freeze_genes = freeze_genes
+        self.process_group, self.shared_seed = process_group, shared_seed
+        self.engine = new_engine(*X.shape)
+        if process_group is not None:
+            from .engine import ShardedEngine
+            self.engine = ShardedEngine(self.engine, process_group)
+        try:
+            self.engine.set_coo(X.row, X.col, X.data)
+            self.engine.set_hyper(*hyper)
+            self.engine.set_state(**state)
+        except Exception:
+            self.close()
+            raise
+
+    def run(self, t, n, reinit):
+        """iterations t .. t+n-1"""
+        if n > 0 and t == 0 and reinit:
+            if self.process_group is not None:
+                self.engine.step(1, random_phi_seed=self.shared_seed(self.process_group), **self.flags)
+            else:
+                _random_phi_step(self.engine, self.X.data, self.nfactors, **self.flags)
+            n -= 1
+        if n > 0:
+            self.engine.step(n, **self.flags)
+
+    def loss(self):
+        return self.engine.loss()
+
+    def host_state(self):
+        """{name: (vi_shape, vi_rate)}; the gene side is absent when it is frozen"""
+        return self.engine.get_state(("theta", "xi") if self.freeze_genes else ("theta", "beta", "xi", "eta"))
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+
+
+class MinibatchLoop(object):
+    """`batchsize` cells per iteration, on the device.
+
+    The reference slices `X.tocsr()[batch_ix, :].tocoo()` on the host every iteration and runs
+    its kernels on that submatrix (scHPF_.py:642-650).  Here a batch is an engine of its own
+    over the batch's rows (re-based to 0..batchsize-1, all genes): its sweeps and
+    finalisations are the full-batch kernels, in the `batched` order of scHPF_.py:686-704
+    (theta/xi first, then beta from the same Xphi with the NEW theta in its rate;
+    SCHPF_CELLS_FIRST).  theta/xi of all cells live on the host between iterations (a batch
+    moves 4*batchsize*K doubles); beta/eta stay on the device and are handed from one
+    batch's engine to the next device-to-device.  The batch schedule is a fixed cyclic
+    sequence of windows over one shuffled cell order, so while there are few distinct
+    windows each keeps its engine and device layout; otherwise one engine is re-laid out
+    every iteration.  The loss is taken by a full-matrix engine that is only built if the
+    default loss is used.
+    """
+
+    def __init__(self, new_engine, X, hyper, state, nfactors, batchsize, freeze_genes, simultaneous):
+        self.new_engine, self.hyper, self.nfactors = new_engine, hyper, nfactors
+        self.ncells, self.ngenes = X.shape
+        self.batchsize = int(batchsize)
+        self.freeze_genes = freeze_genes
+        self.flags = dict(freeze_genes=freeze_genes, simultaneous=simultaneous, cells_first=True)
+        self.X = X
+        # like the reference's X.tocsr(): duplicates summed, columns sorted within a row
+        self.Xcsr = X.tocsr()
+        f = lambda pair: [np.array(pair[0], dtype=np.float64, copy=True), np.array(pair[1], dtype=np.float64, copy=True)]
+        self.theta, self.xi = f(state["theta"]), f(state["xi"])
+        self._gene_init = dict(beta=state["beta"], eta=state["eta"])
+        self.windows = minibatch_windows(self.ncells, self.batchsize)
+        n_windows = self.ncells // gcd(self.ncells, self.batchsize)
+        self.cache_engines = n_windows <= MINIBATCH_ENGINE_CACHE
+        self.engines = {}          # window start -> engine (only one entry when not caching)
+        self.current = None        # the engine holding the newest beta / eta
+        self.full = None
+
+    # -- engines -------------------------------------------------------------
+    def _batch_engine(self, start, batch_ix):
+        key = start if self.cache_engines else 0
+        eng, Xb = self.engines.get(key), None
+        if eng is None or not self.cache_engines:
+            Xb = self.Xcsr[batch_ix, :].tocoo()
+            if eng is None:
+                eng = self.new_engine(self.batchsize, self.ngenes)
+                eng.set_hyper(*self.hyper)
+                self.engines[key] = eng
+            eng.set_coo(Xb.row, Xb.col, Xb.data)
+        if self.current is None:
+            eng.set_state(**self._gene_init)
+        elif eng is not self.current:
+            eng.copy_gene_state_from(self.current)
+        return eng, Xb
+
+    def run(self, t, n, reinit):
+        for tt in range(t, t + n):
+            start, batch_ix = next(self.windows)
+            eng, Xb = self._batch_engine(start, batch_ix)
+            eng.set_state(theta=(self.theta[0][batch_ix], self.theta[1][batch_ix]),
+                          xi=(self.xi[0][batch_ix], self.xi[1][batch_ix]))
+            if tt == 0 and reinit:
+                if Xb is None:
+                    Xb = self.Xcsr[batch_ix, :].tocoo()
+                _random_phi_step(eng, Xb.data, self.nfactors, **self.flags)
+            else:
+                eng.step(1, **self.flags)
+            st = eng.get_state(("theta", "xi"))
+            for k in (0, 1):
+                self.theta[k][batch_ix] = st["theta"][k]
+                self.xi[k][batch_ix] = st["xi"][k]
+            self.current = eng
+
+    # -- read-outs -------------------------------------------------------------
+    def loss(self):
+        """mean negative Poisson llh of ALL of X (the reference's default loss is bound to the
+        whole training matrix, scHPF_.py:622-624) under the current state."""
+        if self.full is None:
+            self.full = self.new_engine(self.ncells, self.ngenes)
+            self.full.set_hyper(*self.hyper)
+            self.full.set_coo(self.X.row, self.X.col, self.X.data)
+        self.full.set_state(theta=tuple(self.theta), xi=tuple(self.xi))
+        if self.current is None:
+            self.full.set_state(**self._gene_init)
+        else:
+            self.full.copy_gene_state_from(self.current)
+        return self.full.loss()
+
+    def host_state(self):
+        out = {"theta": (self.theta[0].copy(), self.theta[1].copy()),
+               "xi": (self.xi[0].copy(), self.xi[1].copy())}
+        if not self.freeze_genes:
+            if self.current is None:
+                out.update({k: (np.array(v[0], dtype=np.float64), np.array(v[1], dtype=np.float64))
+                            for k, v in self._gene_init.items()})
+            else:
+                out.update(self.current.get_state(("beta", "eta")))
+        return out
+
+    def close(self):
+        for eng in list(self.engines.values()) + ([self.full] if self.full is not None else []):
+            eng.close()
+        self.engines, self.full, self.current = {}, None, None

@@ -351,7 +351,12 @@ int step_end_impl(schpf_engine *h, int flags)
 {
     const bool freeze = flags & SCHPF_FREEZE_GENES;
     const bool simultaneous = flags & SCHPF_SIMULTANEOUS;
+    const bool cells_first = flags & SCHPF_CELLS_FIRST;
     const int K = h->K;
+    if (cells_first && h->comm && !freeze) {
+        set_error("SCHPF_CELLS_FIRST (minibatch order) is not available on a sharded engine");
+        return SCHPF_ERR_ARG;
+    }
     auto theta_update = [&]() -> int {
         // scHPF_.py:709-714: theta shape from the row sums, rate from xi (old) + column sums of
         // beta.e_x, then xi rate; also next iteration's tables and theta.e_x column sums
@@ -375,6 +380,15 @@ int step_end_impl(schpf_engine *h, int flags)
         // scHPF_.py:666-684: cell updates see the OLD beta, gene updates the OLD theta
         RC_TRY(theta_update());
         if (!freeze) RC_TRY(beta_update());
+    } else if (cells_first) {
+        // scHPF_.py:686-704 (`batched`): cell updates first, from the OLD beta; beta's rate then sums
+        // theta.e_x of the NEW theta, which theta_update has just left in colsum_t_next
+        RC_TRY(theta_update());
+        if (!freeze) {
+            CUDA_TRY(cudaMemcpyAsync(h->exch + (size_t)h->G * K, h->colsum_t_next, sizeof(double) * K,
+                                     cudaMemcpyDeviceToDevice, h->stream));
+            RC_TRY(beta_update());
+        }
     } else {
         if (!freeze) RC_TRY(beta_update());
         RC_TRY(theta_update());
@@ -691,6 +705,32 @@ int schpf_get_state(schpf_engine_t *h, double *theta_shp, double *theta_rte, dou
     if (eta_shp) RC_TRY(download(eta_shp, h->eta_shp, h->G, h->stream));
     if (eta_rte) RC_TRY(download(eta_rte, h->eta_rte, h->G, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return SCHPF_OK;
+}
+
+int schpf_copy_gene_state(schpf_engine_t *dst, schpf_engine_t *src)
+{
+    RC_TRY(check_handle(src));
+    RC_TRY(check_handle(dst));
+    if (dst == src) return SCHPF_OK;
+    if (dst->device != src->device || dst->G != src->G || dst->K != src->K) {
+        set_error("schpf_copy_gene_state: handles differ (device %d/%d, ngenes %lld/%lld, nfactors %d/%d)",
+                  dst->device, src->device, (long long)dst->G, (long long)src->G, dst->K, src->K);
+        return SCHPF_ERR_ARG;
+    }
+    if (!src->have_state) {
+        set_error("schpf_copy_gene_state: source engine has no state");
+        return SCHPF_ERR_STATE;
+    }
+    // the two handles may use different streams: finish the source's work first
+    CUDA_TRY(cudaStreamSynchronize(src->stream));
+    const size_t GK = sizeof(double) * (size_t)dst->G * dst->K, Gb = sizeof(double) * (size_t)dst->G;
+    CUDA_TRY(cudaMemcpyAsync(dst->beta_shp, src->beta_shp, GK, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->beta_rte, src->beta_rte, GK, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->eta_shp, src->eta_shp, Gb, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->eta_rte, src->eta_rte, Gb, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaStreamSynchronize(dst->stream));   // src may be stepped again right away
+    dst->tables_b_valid = false;
     return SCHPF_OK;
 }
 

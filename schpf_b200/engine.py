@@ -11,13 +11,16 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import FREEZE_GENES, SIMULTANEOUS, as_f64, as_i32, c_i64, c_int, c_dbl, c_u64, c_vp, dptr
+from ._lib import CELLS_FIRST, FREEZE_GENES, SIMULTANEOUS, as_f64, as_i32, c_i64, c_int, c_dbl, c_u64, c_vp, dptr
 
 STATE_NAMES = ("theta", "beta", "xi", "eta")
 
 
-def _flags(freeze_genes, simultaneous):
-    return (FREEZE_GENES if freeze_genes else 0) | (SIMULTANEOUS if simultaneous else 0)
+def _flags(freeze_genes, simultaneous, cells_first=False):
+    """`cells_first` is the minibatch order of scHPF_.py:686-704; `simultaneous` wins over it,
+    as in the reference (:666)."""
+    return ((FREEZE_GENES if freeze_genes else 0) | (SIMULTANEOUS if simultaneous else 0)
+            | (CELLS_FIRST if cells_first and not simultaneous else 0))
 
 
 class CaviEngine(object):
@@ -115,18 +118,24 @@ class CaviEngine(object):
         return out
 
     # -- iterations --------------------------------------------------------
-    def step(self, n_iters=1, freeze_genes=False, simultaneous=False):
-        _lib.check(self._lib.schpf_step(self._h, c_int(int(n_iters)), c_int(_flags(freeze_genes, simultaneous))))
+    def step(self, n_iters=1, freeze_genes=False, simultaneous=False, cells_first=False):
+        _lib.check(self._lib.schpf_step(self._h, c_int(int(n_iters)),
+                                        c_int(_flags(freeze_genes, simultaneous, cells_first))))
 
-    def step_with_xphi(self, xphi, freeze_genes=False, simultaneous=False):
+    def step_with_xphi(self, xphi, freeze_genes=False, simultaneous=False, cells_first=False):
         xphi = as_f64(xphi)
         if xphi.shape != (self.nnz, self.nfactors):
             raise ValueError("Xphi must be (nnz, nfactors)")
-        _lib.check(self._lib.schpf_step_with_xphi(self._h, dptr(xphi), c_int(_flags(freeze_genes, simultaneous))))
+        _lib.check(self._lib.schpf_step_with_xphi(self._h, dptr(xphi),
+                                                  c_int(_flags(freeze_genes, simultaneous, cells_first))))
 
-    def step_random_phi(self, seed, freeze_genes=False, simultaneous=False):
+    def step_random_phi(self, seed, freeze_genes=False, simultaneous=False, cells_first=False):
         _lib.check(self._lib.schpf_step_random_phi(self._h, c_u64(int(seed) & (2 ** 64 - 1)),
-                                                   c_int(_flags(freeze_genes, simultaneous))))
+                                                   c_int(_flags(freeze_genes, simultaneous, cells_first))))
+
+    def copy_gene_state_from(self, other):
+        """beta / eta of `other` (same device, ngenes, nfactors) -> this engine, device to device."""
+        _lib.check(self._lib.schpf_copy_gene_state(self._h, other._h))
 
     def step_begin(self, freeze_genes=False, simultaneous=False, random_phi_seed=None):
         mode, seed = (0, 0) if random_phi_seed is None else (1, int(random_phi_seed) & (2 ** 64 - 1))

@@ -19,14 +19,11 @@ from sklearn.base import BaseEstimator
 import joblib
 
 from . import loss as ls
+from .cavi_loop import FullBatchLoop, MinibatchLoop
 from .engine import CaviEngine
 
 # tests substitute an oracle-backed engine here; product code never does
 _engine_factory = None
-
-# nnz * K above which the t == 0 random-phi draw moves from numpy (bit-compatible
-# with a seeded reference run, scHPF_.py:652-655) to the device generator
-HOST_DIRICHLET_LIMIT = 1 << 24
 
 
 # ---- helpers for cell-sharded fits (torch.distributed; any backend) ----------------
@@ -303,6 +300,9 @@ class scHPF(BaseEstimator):
         scHPF_.py:526-604.  `single_process` is accepted and ignored (there is
         one device path).
 
+        `batchsize` cells per iteration run as `cavi_loop.MinibatchLoop` (same kernels on the
+        batch's rows, the reference's `batched` update order).
+
         `process_group` (the only addition): a torch.distributed group whose ranks each pass
         their own contiguous shard of the cells as `X` (all genes).  b', d' come from the whole
         matrix, eta/beta are rank 0's draws on every rank, the loss is the loss over all
@@ -310,10 +310,10 @@ class scHPF(BaseEstimator):
         assert loss_smoothing > 0
         nfactors, (ncells, ngenes) = self.nfactors, X.shape
         a, ap, c, cp = self.a, self.ap, self.c, self.cp
-        if batchsize is not None and 1 < batchsize <= ncells:
-            raise NotImplementedError(
-                'minibatch CAVI (batchsize) is not part of the device loop yet; '
-                'use batchsize=None (DESIGN.md, out of scope)')
+        batched = batchsize is not None and 1 < batchsize <= ncells       # scHPF_.py:627
+        if batched and process_group is not None:
+            raise NotImplementedError('minibatches (batchsize) and cell sharding (process_group) '
+                                      'cannot be combined')
 
         bp, dp, xi, eta, theta, beta = self._setup(X, freeze_genes, reinit, process_group=process_group)
         # capacity shapes are constants of the fit (scHPF_.py:614-618)
@@ -327,19 +327,18 @@ class scHPF(BaseEstimator):
         check_freq = self.check_freq if check_freq is None else check_freq
         verbose = self.verbose if verbose is None else verbose
 
-        engine = self._new_engine(ncells, ngenes)
-        if process_group is not None:
-            from .engine import ShardedEngine
-            engine = ShardedEngine(engine, process_group)
+        hyper = (a, ap, bp, c, cp, dp)
+        state = dict(theta=(theta.vi_shape, theta.vi_rate), beta=(beta.vi_shape, beta.vi_rate),
+                     xi=(xi.vi_shape, xi.vi_rate), eta=(eta.vi_shape, eta.vi_rate))
+        if batched:
+            loop = MinibatchLoop(self._new_engine, X, hyper, state, nfactors, batchsize,
+                                 freeze_genes, beta_theta_simultaneous)
+        else:
+            loop = FullBatchLoop(self._new_engine, X, hyper, state, nfactors, freeze_genes,
+                                 beta_theta_simultaneous, process_group, _shared_seed)
         try:
-            engine.set_coo(X.row, X.col, X.data)
-            engine.set_hyper(a, ap, bp, c, cp, dp)
-            engine.set_state(theta=(theta.vi_shape, theta.vi_rate), beta=(beta.vi_shape, beta.vi_rate),
-                             xi=(xi.vi_shape, xi.vi_rate), eta=(eta.vi_shape, eta.vi_rate))
-
             def host_state():
-                which = ("theta", "xi") if freeze_genes else ("theta", "beta", "xi", "eta")
-                st = engine.get_state(which)
+                st = loop.host_state()
                 wrap = lambda pair: HPF_Gamma(pair[0].astype(self.dtype, copy=False),
                                               pair[1].astype(self.dtype, copy=False))
                 return (wrap(st["xi"]), eta if freeze_genes else wrap(st["eta"]),
@@ -352,24 +351,7 @@ class scHPF(BaseEstimator):
             while t < n_total:
                 next_check = t if t % check_freq == 0 else (t // check_freq + 1) * check_freq
                 last = min(next_check, n_total - 1)
-                n = last - t + 1
-                if t == 0 and reinit:
-                    # first iteration from a random phi instead of the E-step (:652-655)
-                    nnz = X.data.shape[0]
-                    if process_group is not None:
-                        engine.step(1, freeze_genes=freeze_genes, simultaneous=beta_theta_simultaneous,
-                                    random_phi_seed=_shared_seed(process_group))
-                    elif nnz * nfactors <= HOST_DIRICHLET_LIMIT:
-                        random_phi = np.random.dirichlet(np.ones(nfactors), nnz)
-                        engine.step_with_xphi(X.data[:, None] * random_phi, freeze_genes=freeze_genes,
-                                              simultaneous=beta_theta_simultaneous)
-                    else:
-                        engine.step_random_phi(int(np.random.randint(0, 2 ** 31 - 1)),
-                                               freeze_genes=freeze_genes,
-                                               simultaneous=beta_theta_simultaneous)
-                    n -= 1
-                if n > 0:
-                    engine.step(n, freeze_genes=freeze_genes, simultaneous=beta_theta_simultaneous)
+                loop.run(t, last - t + 1, reinit)
                 t = last + 1
                 if last % check_freq != 0:
                     continue
@@ -377,7 +359,7 @@ class scHPF(BaseEstimator):
                 # ---- loss bookkeeping and stopping rules (scHPF_.py:717-774) ----
                 tc = last
                 if loss_function is None:
-                    curr = engine.loss()
+                    curr = loop.loss()
                 else:
                     hxi, heta, htheta, hbeta = host_state()
                     curr = loss_function(a=a, ap=ap, bp=bp, c=c, cp=cp, dp=dp,
@@ -417,7 +399,7 @@ class scHPF(BaseEstimator):
 
             xi, eta, theta, beta = host_state()
         finally:
-            engine.close()
+            loop.close()
         return (bp, dp, xi, eta, theta, beta, loss)
 
     # ---- setup (host, bit-identical to the reference) ------------------------

@@ -43,6 +43,11 @@ def g_simul():
     return load_golden("simul_small.npz")
 
 
+@pytest.fixture(scope="session")
+def g_minibatch():
+    return load_golden("minibatch_small.npz")
+
+
 def has_cuda():
     try:
         import torch

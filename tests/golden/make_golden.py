@@ -23,6 +23,9 @@ Fixtures
   reinit_small.npz  fit with reinit=True (the t==0 Dirichlet branch) under a
                     fixed numpy seed: final state + loss.
   simul_small.npz   beta_theta_simultaneous=True variant of the loop.
+  minibatch_small.npz  scHPF.fit(batchsize=...) (schpf/scHPF_.py:626-631, 642-650, 686-704):
+                    A: reinit=True, 240 cells in windows of 64 (wrapping), 9 iterations;
+                    B: reinit=False, windows of 100, beta_theta_simultaneous, loss_smoothing=2.
 """
 import os
 import sys
@@ -169,11 +172,37 @@ def simul_small():
     print("simul_small: loss", base.loss)
 
 
+def minibatch_small():
+    X = synth_coo(240, 300, 40, 3, seed=5)
+    out = dict(row=X.row.astype(np.int32), col=X.col.astype(np.int32),
+               data=X.data.astype(np.int32), shape=np.array(X.shape))
+    # A: everything from the numpy stream (init, batch shuffle, t == 0 Dirichlet of the batch)
+    np.random.seed(21)
+    m = scHPF(3, verbose=False)
+    m.fit(X, batchsize=64, min_iter=9, max_iter=9, check_freq=2, verbose=False)
+    out.update(A_seed=21, A_batchsize=64, A_iters=9, A_check_freq=2, A_bp=m.bp, A_dp=m.dp,
+               A_loss=np.array(m.loss))
+    out.update(state_dict(m, "A_"))
+    # B: seeded init, then only the shuffle comes from the stream
+    np.random.seed(22)
+    base = scHPF(3, verbose=False)
+    base._initialize(X)
+    out.update(dict(a=base.a, ap=base.ap, bp=base.bp, c=base.c, cp=base.cp, dp=base.dp))
+    out.update(state_dict(base, "B_init_"))
+    np.random.seed(23)
+    base.fit(X, reinit=False, batchsize=100, min_iter=8, max_iter=8, check_freq=2, verbose=False,
+             beta_theta_simultaneous=True, loss_smoothing=2)
+    out.update(B_seed=23, B_batchsize=100, B_iters=8, B_check_freq=2, B_loss=np.array(base.loss))
+    out.update(state_dict(base, "B_"))
+    np.savez_compressed(os.path.join(HERE, "minibatch_small.npz"), **out)
+    print("minibatch_small: loss A", m.loss, "loss B", base.loss)
+
+
 if __name__ == "__main__":
-    kernels_k4()
-    cavi_cfg1()
-    reinit_small()
-    simul_small()
+    only = sys.argv[1:]
+    for fn in (kernels_k4, cavi_cfg1, reinit_small, simul_small, minibatch_small):
+        if not only or fn.__name__ in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -56,22 +56,26 @@ class OracleEngine(object):
         return {k: (v[0].copy(), v[1].copy()) for k, v in full.items() if k in which}
 
     # ---- whole iterations --------------------------------------------------
-    def _iter(self, freeze_genes, simultaneous, Xphi=None):
+    def _iter(self, freeze_genes, simultaneous, Xphi=None, cells_first=False):
         onp.cavi_iteration(self.data, self.row, self.col, self.st, self.a, self.bp, self.c, self.dp,
                            freeze_genes=freeze_genes, Xphi=Xphi,
-                           beta_theta_simultaneous=simultaneous)
+                           beta_theta_simultaneous=simultaneous, batched=cells_first)
 
-    def step(self, n_iters=1, freeze_genes=False, simultaneous=False):
+    def step(self, n_iters=1, freeze_genes=False, simultaneous=False, cells_first=False):
         for _ in range(int(n_iters)):
-            self._iter(freeze_genes, simultaneous)
+            self._iter(freeze_genes, simultaneous, cells_first=cells_first)
 
-    def step_with_xphi(self, xphi, freeze_genes=False, simultaneous=False):
-        self._iter(freeze_genes, simultaneous, Xphi=np.asarray(xphi, dtype=np.float64))
+    def step_with_xphi(self, xphi, freeze_genes=False, simultaneous=False, cells_first=False):
+        self._iter(freeze_genes, simultaneous, Xphi=np.asarray(xphi, dtype=np.float64), cells_first=cells_first)
 
-    def step_random_phi(self, seed, freeze_genes=False, simultaneous=False):
+    def step_random_phi(self, seed, freeze_genes=False, simultaneous=False, cells_first=False):
         rng = np.random.default_rng(seed)
         phi = rng.dirichlet(np.ones(self.nfactors), self.nnz)
-        self._iter(freeze_genes, simultaneous, Xphi=self.data[:, None] * phi)
+        self._iter(freeze_genes, simultaneous, Xphi=self.data[:, None] * phi, cells_first=cells_first)
+
+    def copy_gene_state_from(self, other):
+        o = other.st
+        self.set_state(beta=(o.beta_shp, o.beta_rte), eta=(o.eta_shp, o.eta_rte))
 
     # ---- split phase (cell sharding) ----------------------------------------
     def step_begin(self, freeze_genes=False, simultaneous=False, random_phi_seed=None):

@@ -1,0 +1,174 @@
+"""GPU parity of the minibatch loop (scHPF_.py:626-631, 642-650, 686-704): the
+`batched` update order on the device (SCHPF_CELLS_FIRST), the device-to-device
+hand-over of beta / eta between batch engines, and `scHPF.fit(batchsize=...)`
+against golden runs of the real reference (tests/golden/minibatch_small.npz)
+and against the oracle on a larger seeded problem."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_equal
+from scipy.sparse import coo_matrix
+
+from schpf_b200 import scHPF, HPF_Gamma, cavi_loop
+from schpf_b200.engine import CaviEngine
+from schpf_b200._lib import SchpfError
+from conftest import max_rel
+from oracle import hpf_numpy as onp
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ("theta", "beta", "xi", "eta")
+TOL = 1e-9
+HYP = (0.3, 1.0, 0.7, 0.3, 1.0, 1.3)
+
+
+def _X(g):
+    return coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(int(v) for v in g["shape"]))
+
+
+def _gam(g, name, prefix):
+    return HPF_Gamma(g[prefix + name + "_shp"].copy(), g[prefix + name + "_rte"].copy())
+
+
+def _problem(C, G, K, nnz, seed):
+    rng = np.random.default_rng(seed)
+    row = rng.integers(0, C, nnz).astype(np.int32)
+    col = rng.integers(0, G, nnz).astype(np.int32)
+    data = rng.integers(1, 30, nnz).astype(np.int32)
+    st = onp.State(rng.uniform(0.15, 0.45, (C, K)), rng.uniform(0.5, 1.5, (C, K)),
+                   rng.uniform(0.15, 0.45, (G, K)), rng.uniform(0.5, 1.5, (G, K)),
+                   np.full(C, 1.0 + K * 0.3), rng.uniform(0.5, 1.5, C),
+                   np.full(G, 1.0 + K * 0.3), rng.uniform(0.5, 1.5, G))
+    return row, col, data, st
+
+
+def _load(e, row, col, data, st):
+    e.set_coo(row, col, data)
+    e.set_hyper(*HYP)
+    e.set_state(theta=(st.theta_shp, st.theta_rte), beta=(st.beta_shp, st.beta_rte),
+                xi=(st.xi_shp, st.xi_rte), eta=(st.eta_shp, st.eta_rte))
+
+
+@pytest.mark.parametrize("K", [3, 20, 33])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_cells_first_order_against_oracle(K, variant):
+    """theta/xi first from the old beta; beta's rate from the NEW theta (scHPF_.py:686-704)."""
+    row, col, data, st = _problem(211, 157, K, 5000, 10 + K)
+    with CaviEngine(211, 157, K, variant=variant, panel_rows=64) as e:
+        _load(e, row, col, data, st)
+        e.step(4, cells_first=True)
+        got = e.get_state()
+    for _ in range(4):
+        onp.cavi_iteration(data, row, col, st, HYP[0], HYP[2], HYP[3], HYP[5], batched=True)
+    want = dict(theta=(st.theta_shp, st.theta_rte), beta=(st.beta_shp, st.beta_rte),
+                xi=(st.xi_shp, st.xi_rte), eta=(st.eta_shp, st.eta_rte))
+    for n in NAMES:
+        assert max_rel(got[n][0], want[n][0]) < TOL and max_rel(got[n][1], want[n][1]) < TOL, n
+    # the order matters: the default order gives a different beta rate
+    row, col, data, st2 = _problem(211, 157, K, 5000, 10 + K)
+    for _ in range(4):
+        onp.cavi_iteration(data, row, col, st2, HYP[0], HYP[2], HYP[3], HYP[5])
+    assert max_rel(st2.beta_rte, st.beta_rte) > 1e-6
+
+
+def test_cells_first_with_frozen_genes_and_simultaneous_flag():
+    row, col, data, st = _problem(120, 90, 6, 2500, 5)
+    with CaviEngine(120, 90, 6) as e:
+        _load(e, row, col, data, st)
+        e.step(3, freeze_genes=True, cells_first=True)
+        got = e.get_state()
+    assert_equal(got["beta"][0], st.beta_shp)
+    assert_equal(got["eta"][1], st.eta_rte)
+    for _ in range(3):
+        onp.cavi_iteration(data, row, col, st, HYP[0], HYP[2], HYP[3], HYP[5], freeze_genes=True, batched=True)
+    assert max_rel(got["theta"][0], st.theta_shp) < TOL and max_rel(got["xi"][1], st.xi_rte) < TOL
+    # simultaneous wins over cells_first, as in the reference (:666)
+    row, col, data, st = _problem(120, 90, 6, 2500, 6)
+    with CaviEngine(120, 90, 6) as e:
+        _load(e, row, col, data, st)
+        e.step(2, simultaneous=True, cells_first=True)
+        got = e.get_state()
+    for _ in range(2):
+        onp.cavi_iteration(data, row, col, st, HYP[0], HYP[2], HYP[3], HYP[5], beta_theta_simultaneous=True)
+    assert max_rel(got["beta"][1], st.beta_rte) < TOL and max_rel(got["theta"][1], st.theta_rte) < TOL
+
+
+def test_copy_gene_state_between_engines():
+    row, col, data, st = _problem(80, 64, 5, 1500, 1)
+    row2, col2, data2, st2 = _problem(33, 64, 5, 700, 2)
+    with CaviEngine(80, 64, 5) as a, CaviEngine(33, 64, 5) as b, CaviEngine(33, 65, 5) as wrong:
+        _load(a, row, col, data, st)
+        a.step(2)
+        _load(b, row2, col2, data2, st2)
+        b.copy_gene_state_from(a)
+        ga, gb = a.get_state(("beta", "eta")), b.get_state()
+        for n in ("beta", "eta"):
+            assert_equal(gb[n][0], ga[n][0])            # bit-exact: it is a copy
+            assert_equal(gb[n][1], ga[n][1])
+        assert_equal(gb["theta"][0], st2.theta_shp)     # the cell side is untouched
+        # the copied beta is what the next step of b uses (tables are rebuilt from it)
+        b.step(1, cells_first=True)
+        got = b.get_state()
+        st2.beta_shp, st2.beta_rte = ga["beta"][0].copy(), ga["beta"][1].copy()
+        st2.eta_shp, st2.eta_rte = ga["eta"][0].copy(), ga["eta"][1].copy()
+        onp.cavi_iteration(data2, row2, col2, st2, HYP[0], HYP[2], HYP[3], HYP[5], batched=True)
+        assert max_rel(got["beta"][0], st2.beta_shp) < TOL and max_rel(got["theta"][1], st2.theta_rte) < TOL
+        with pytest.raises(SchpfError):
+            wrong.copy_gene_state_from(a)               # ngenes differ
+
+
+@pytest.mark.parametrize("cache", [64, 0])
+def test_minibatch_fit_matches_seeded_reference(g_minibatch, monkeypatch, cache):
+    """Case A: init, shuffle and the batch's t == 0 Dirichlet from numpy's stream, 240 cells in
+    wrapping windows of 64; with per-window engines and with one engine re-laid out per step."""
+    monkeypatch.setattr(cavi_loop, "MINIBATCH_ENGINE_CACHE", cache)
+    g, X = g_minibatch, _X(g_minibatch)
+    np.random.seed(int(g["A_seed"]))
+    m = scHPF(3, verbose=False).fit(X, batchsize=int(g["A_batchsize"]), min_iter=int(g["A_iters"]),
+                                    max_iter=int(g["A_iters"]), check_freq=int(g["A_check_freq"]))
+    for n in NAMES:
+        assert max_rel(getattr(m, n).vi_shape, g["A_%s_shp" % n]) < TOL, n
+        assert max_rel(getattr(m, n).vi_rate, g["A_%s_rte" % n]) < TOL, n
+    assert_allclose(m.loss, g["A_loss"], rtol=1e-11)
+
+
+def test_minibatch_simultaneous_matches_reference(g_minibatch):
+    g, X = g_minibatch, _X(g_minibatch)
+    m = scHPF(3, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]),
+              xi=_gam(g, "xi", "B_init_"), theta=_gam(g, "theta", "B_init_"),
+              eta=_gam(g, "eta", "B_init_"), beta=_gam(g, "beta", "B_init_"))
+    np.random.seed(int(g["B_seed"]))
+    m.fit(X, reinit=False, batchsize=int(g["B_batchsize"]), min_iter=int(g["B_iters"]),
+          max_iter=int(g["B_iters"]), check_freq=int(g["B_check_freq"]),
+          beta_theta_simultaneous=True, loss_smoothing=2)
+    for n in NAMES:
+        assert max_rel(getattr(m, n).vi_shape, g["B_%s_shp" % n]) < TOL, n
+        assert max_rel(getattr(m, n).vi_rate, g["B_%s_rte" % n]) < TOL, n
+    assert_allclose(m.loss, g["B_loss"], rtol=1e-11)
+
+
+def test_minibatch_larger_problem_against_oracle_loop():
+    """3000 x 800, K = 20, windows of 700 (gcd 100 -> 30 windows, wraps), 12 iterations from a
+    fixed init: the device loop against the same loop driven through the oracle."""
+    from schpf_b200 import scHPF_ as shell
+    from schpf_b200.synth import synth_coo
+    from oracle_engine import OracleEngine
+    X = synth_coo(3000, 800, 60, 20, seed=3)
+    np.random.seed(8)
+    base = scHPF(20, verbose=False)
+    base._initialize(X)
+    runs = []
+    for factory in (None, OracleEngine):
+        shell._engine_factory = factory
+        try:
+            from copy import deepcopy
+            m = deepcopy(base)
+            np.random.seed(9)
+            m.fit(X, reinit=False, batchsize=700, min_iter=12, max_iter=12, check_freq=4)
+            runs.append(m)
+        finally:
+            shell._engine_factory = None
+    dev, ora = runs
+    for n in NAMES:
+        assert max_rel(getattr(dev, n).vi_shape, getattr(ora, n).vi_shape) < TOL, n
+        assert max_rel(getattr(dev, n).vi_rate, getattr(ora, n).vi_rate) < TOL, n
+    assert_allclose(dev.loss, ora.loss, rtol=1e-11)

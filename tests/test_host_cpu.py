@@ -199,8 +199,79 @@ def test_checkstep_function_and_custom_loss_get_host_state(oracle_backend, g_cav
     np.random.seed(0)
     m = scHPF(5, verbose=False).fit(X, max_iter=7, min_iter=7, check_freq=3, checkstep_function=checkstep)
     assert seen == [0, 3, 6] and len(m.loss) == 3
-    with pytest.raises(NotImplementedError):
-        scHPF(5, verbose=False).fit(X, batchsize=100, max_iter=2)
+
+
+# ------------------------------------------------------------- minibatches ---
+def test_minibatch_windows_follow_the_reference_schedule():
+    """util.py:218-231: one shuffle, then consecutive wrapping windows."""
+    from schpf_b200.cavi_loop import minibatch_windows
+    np.random.seed(4)
+    order = np.arange(10)
+    np.random.shuffle(order)
+    np.random.seed(4)
+    gen = minibatch_windows(10, 4)
+    got = [next(gen) for _ in range(6)]
+    assert [s for s, _ in got] == [0, 4, 8, 2, 6, 0]
+    assert_equal(got[0][1], order[0:4])
+    assert_equal(got[2][1], np.concatenate([order[8:], order[:2]]))       # wraps
+    assert_equal(got[5][1], order[0:4])                                  # the cycle repeats
+    np.random.seed(4)
+    gen = minibatch_windows(10, 10)                                      # equality is allowed (:219)
+    assert_equal(next(gen)[1], order)
+    assert_equal(next(gen)[1], order)
+
+
+@pytest.mark.parametrize("cache", [64, 0])
+def test_minibatch_fit_reproduces_seeded_reference(oracle_backend, g_minibatch, monkeypatch, cache):
+    """Case A of minibatch_small.npz: init, batch shuffle and the batch's t == 0 Dirichlet all
+    come from numpy's stream in the reference's order; with and without per-window engines."""
+    from schpf_b200 import cavi_loop
+    monkeypatch.setattr(cavi_loop, "MINIBATCH_ENGINE_CACHE", cache)
+    g, X = g_minibatch, _X(g_minibatch)
+    np.random.seed(int(g["A_seed"]))
+    m = scHPF(3, verbose=False).fit(X, batchsize=int(g["A_batchsize"]), min_iter=int(g["A_iters"]),
+                                    max_iter=int(g["A_iters"]), check_freq=int(g["A_check_freq"]))
+    assert m.bp == float(g["A_bp"]) and m.dp == float(g["A_dp"])
+    for name in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(m, name).vi_shape, g["A_%s_shp" % name]) < 1e-11
+        assert max_rel(getattr(m, name).vi_rate, g["A_%s_rte" % name]) < 1e-11
+    assert_allclose(m.loss, g["A_loss"], rtol=1e-12)
+
+
+def test_minibatch_simultaneous_and_smoothing(oracle_backend, g_minibatch):
+    """Case B: reinit=False, beta_theta_simultaneous, loss_smoothing=2."""
+    g, X = g_minibatch, _X(g_minibatch)
+    m = scHPF(3, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]),
+              xi=_gam(g, "xi", "B_init_"), theta=_gam(g, "theta", "B_init_"),
+              eta=_gam(g, "eta", "B_init_"), beta=_gam(g, "beta", "B_init_"))
+    np.random.seed(int(g["B_seed"]))
+    m.fit(X, reinit=False, batchsize=int(g["B_batchsize"]), min_iter=int(g["B_iters"]),
+          max_iter=int(g["B_iters"]), check_freq=int(g["B_check_freq"]),
+          beta_theta_simultaneous=True, loss_smoothing=2)
+    for name in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(m, name).vi_shape, g["B_%s_shp" % name]) < 1e-11
+        assert max_rel(getattr(m, name).vi_rate, g["B_%s_rte" % name]) < 1e-11
+    assert_allclose(m.loss, g["B_loss"], rtol=1e-12)
+
+
+def test_minibatch_edge_cases(oracle_backend, g_minibatch):
+    g, X = g_minibatch, _X(g_minibatch)
+    # batchsize 0 / 1 / None / > ncells mean "all cells" (scHPF_.py:627)
+    np.random.seed(3)
+    full = scHPF(3, verbose=False).fit(X, min_iter=3, max_iter=3, check_freq=1)
+    for bs in (0, 1, None, X.shape[0] + 1):
+        np.random.seed(3)
+        m = scHPF(3, verbose=False).fit(X, batchsize=bs, min_iter=3, max_iter=3, check_freq=1)
+        assert_equal(m.theta.vi_shape, full.theta.vi_shape)
+    # custom loss / checkstep functions see full-size host arrays; frozen genes stay untouched
+    seen = []
+    np.random.seed(3)
+    m = scHPF(3, verbose=False).fit(X, batchsize=50, min_iter=4, max_iter=4, check_freq=2,
+                                    checkstep_function=lambda **k: seen.append((k["t"], k["theta"].dims, k["beta"].dims)))
+    assert seen == [(0, (240, 3), (300, 3)), (2, (240, 3), (300, 3))]
+    np.random.seed(3)
+    p = m.project(X, batchsize=60, min_iter=3, max_iter=3, check_freq=1)
+    assert p.beta == m.beta and p.eta == m.eta and len(p.loss) == 3
 
 
 def test_combine_across_cells(g_kernels):
