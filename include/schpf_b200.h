@@ -55,6 +55,10 @@ int         schpf_version(void);
 const char *schpf_last_error(void);
 /* number of visible CUDA devices, or a negative SCHPF_ERR_* */
 int         schpf_device_count(void);
+/* schpf_set_coo keeps one work area per device between calls (about 32 bytes per nonzero of the
+ * largest matrix seen; growing device allocations by gigabytes costs more than the re-layout
+ * itself).  This frees it; SCHPF_ERR_STATE if a schpf_set_coo is running on that device. */
+int         schpf_release_scratch(int device);
 
 /* ------------------------------------------------------------------------
  * Function level: one entry per reference kernel.  All pointers are HOST.

@@ -25,6 +25,7 @@ SIGNATURES = {
     "schpf_version": [],
     "schpf_last_error": [],
     "schpf_device_count": [],
+    "schpf_release_scratch": [c_int],
     "schpf_psi": [c_int, c_i64, p_dbl, p_dbl],
     "schpf_gammaln": [c_int, c_i64, p_dbl, p_dbl],
     "schpf_compute_Xphi_data": [c_int, c_i64, c_i64, c_i64, c_int, p_i32, p_i32, p_i32,

@@ -223,6 +223,9 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
                       const int32_t *d_oth, const int32_t *d_val, int64_t n_own, int64_t n_oth,
                       int panel_rows, int warps, int target_ctas, bool packed);
 
+// frees the per-device scratch block the layout builds keep between calls
+int release_layout_scratch(int device);
+
 // ------------------------------------------------------------- sweeps ------
 enum SweepMode { SWEEP_SHAPE = 0, SWEEP_LLH = 1 };
 

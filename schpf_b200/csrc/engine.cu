@@ -503,6 +503,8 @@ int schpf_device_count(void)
     return n;
 }
 
+int schpf_release_scratch(int device) { return release_layout_scratch(device); }
+
 int schpf_create(schpf_engine_t **out, int device, int64_t ncells, int64_t ngenes, int nfactors, void *stream)
 {
     if (!out) {

@@ -30,6 +30,8 @@
 // radix sort's stability).
 #include <cub/cub.cuh>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace schpf {
@@ -239,12 +241,76 @@ __global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__
     if (rs[0] | rs[1] | rs[2] | rs[3]) atomicAdd(unplaced, 1);   // schedule incomplete: never expected
 }
 
-struct DevBuf {
+// ---- scratch for the build's temporaries ----------------------------------------
+// One block per device, kept between builds (grow-only; schpf_release_scratch frees it): the
+// temporaries are ~30 B per nonzero, and growing the stream-ordered pool by gigabytes costs
+// 50-500 ms per build (measured, tools/diag_layout.py) against ~50 ms of actual work.
+struct ScratchSlot {
     void *p = nullptr;
+    size_t cap = 0;
+    bool busy = false;
+};
+constexpr int MAX_DEVICES = 64;
+ScratchSlot g_scratch[MAX_DEVICES];
+std::mutex g_scratch_mutex;
+
+struct Scratch {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    int slot = -1;               // >= 0: the device's cached block; -1: a one-off pool allocation
     cudaStream_t stream = nullptr;
-    ~DevBuf() { if (p) pool_free(p, stream); }
-    cudaError_t alloc(size_t bytes) { return pool_malloc(&p, bytes ? bytes : 1, stream); }
-    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+
+    cudaError_t acquire(size_t bytes, cudaStream_t s)
+    {
+        stream = s;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        {
+            std::lock_guard<std::mutex> lock(g_scratch_mutex);
+            if (dev < MAX_DEVICES && !g_scratch[dev].busy) {
+                ScratchSlot &S = g_scratch[dev];
+                if (S.cap < bytes) {
+                    if (S.p) cudaFree(S.p);      // idle: its last user synchronised before releasing
+                    S.p = nullptr;
+                    S.cap = 0;
+                    e = cudaMalloc(&S.p, bytes);
+                    if (e != cudaSuccess) return e;
+                    S.cap = bytes;
+                }
+                S.busy = true;
+                slot = dev;
+                base = static_cast<char *>(S.p);
+                cap = S.cap;
+                return cudaSuccess;
+            }
+        }
+        // another build is using the block (trials on several host threads): one-off allocation
+        void *p = nullptr;
+        e = pool_malloc(&p, bytes, stream);
+        if (e != cudaSuccess) return e;
+        base = static_cast<char *>(p);
+        cap = bytes;
+        return cudaSuccess;
+    }
+    ~Scratch()
+    {
+        if (!base) return;
+        cudaStreamSynchronize(stream);   // also on error paths: nothing may still be using the block
+        if (slot >= 0) {
+            std::lock_guard<std::mutex> lock(g_scratch_mutex);
+            g_scratch[slot].busy = false;
+        } else {
+            pool_free(base, stream);
+        }
+    }
+    static size_t rounded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+    template <typename T> T *take(size_t n)
+    {
+        T *p = reinterpret_cast<T *>(base + used);
+        used += rounded(sizeof(T) * (n ? n : 1));
+        return p;
+    }
 };
 
 int bits_for(uint64_t max_value)
@@ -255,6 +321,24 @@ int bits_for(uint64_t max_value)
 }
 
 }  // namespace
+
+int release_layout_scratch(int device)
+{
+    if (device < 0 || device >= MAX_DEVICES) return SCHPF_OK;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    ScratchSlot &S = g_scratch[device];
+    if (S.busy) {
+        set_error("layout scratch of device %d is in use", device);
+        return SCHPF_ERR_STATE;
+    }
+    if (S.p) {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaFree(S.p));
+    }
+    S.p = nullptr;
+    S.cap = 0;
+    return SCHPF_OK;
+}
 
 void SideLayout::release()
 {
@@ -301,72 +385,70 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&L.own_id), sizeof(int32_t) * n_slots, stream));
     CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&L.seg_ptr), sizeof(int64_t) * n_ptr, stream));
 
-    DevBuf cnt, ids, cnt_sorted, ids_sorted, slot_of, seg_cnt, seg_first, pairs, keys, vals, keys2, vals2, tmp, unplaced;
-    for (DevBuf *b : {&cnt, &ids, &cnt_sorted, &ids_sorted, &slot_of, &seg_cnt, &seg_first, &pairs, &keys, &vals,
-                      &keys2, &vals2, &tmp, &unplaced})
-        b->stream = stream;
-    CUDA_TRY(unplaced.alloc(sizeof(int)));
-    CUDA_TRY(cudaMemsetAsync(unplaced.p, 0, sizeof(int), stream));
-    CUDA_TRY(cnt.alloc(sizeof(int32_t) * n_own));
-    CUDA_TRY(ids.alloc(sizeof(int32_t) * n_own));
-    CUDA_TRY(cnt_sorted.alloc(sizeof(int32_t) * n_own));
-    CUDA_TRY(ids_sorted.alloc(sizeof(int32_t) * n_own));
-    CUDA_TRY(slot_of.alloc(sizeof(int32_t) * n_own));
-    CUDA_TRY(seg_cnt.alloc(sizeof(int64_t) * n_seg));
-    CUDA_TRY(seg_first.alloc(sizeof(int64_t) * n_seg));
-    CUDA_TRY(pairs.alloc(sizeof(int64_t) * n_ptr));
-    CUDA_TRY(keys.alloc(sizeof(uint64_t) * nnz));
-    CUDA_TRY(vals.alloc(sizeof(uint64_t) * nnz));
-    CUDA_TRY(keys2.alloc(sizeof(uint64_t) * nnz));
-    CUDA_TRY(vals2.alloc(sizeof(uint64_t) * nnz));
+    // sizes of the sort / scan work areas first (no device work), then ONE scratch block
+    const int key_bits = KEY_LOCAL_BITS + KEY_ROT_BITS + bits_for((uint64_t)(n_seg > 4 ? n_seg / 4 - 1 : 0));
+    size_t tmp_bytes = 0, need = 0;
+    {
+        cub::DoubleBuffer<int32_t> k32(nullptr, nullptr), v32(nullptr, nullptr);
+        CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, k32, v32, (int)n_own, 0, 32, stream));
+        tmp_bytes = need;
+        cub::DoubleBuffer<uint64_t> k64(nullptr, nullptr), v64(nullptr, nullptr);
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, k64, v64, nnz, 0, key_bits, stream));
+        if (need > tmp_bytes) tmp_bytes = need;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, (int64_t *)nullptr, (int64_t *)nullptr, n_seg, stream));
+        if (need > tmp_bytes) tmp_bytes = need;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, (int64_t *)nullptr, (int64_t *)nullptr, n_ptr, stream));
+        if (need > tmp_bytes) tmp_bytes = need;
+    }
+    const size_t R = 256;   // Scratch::take rounds every piece up to this
+    const size_t total = 5 * (sizeof(int32_t) * n_own + R) + 2 * (sizeof(int64_t) * n_seg + R) +
+                         (sizeof(int64_t) * n_ptr + R) + 4 * (sizeof(uint64_t) * nnz + R) + (tmp_bytes + R) + 2 * R;
+    Scratch scratch;
+    CUDA_TRY(scratch.acquire(total, stream));
+    int *unplaced = scratch.take<int>(1);
+    int32_t *cnt = scratch.take<int32_t>(n_own), *ids = scratch.take<int32_t>(n_own);
+    int32_t *cnt_alt = scratch.take<int32_t>(n_own), *ids_alt = scratch.take<int32_t>(n_own);
+    int32_t *slot_of = scratch.take<int32_t>(n_own);
+    int64_t *seg_cnt = scratch.take<int64_t>(n_seg), *seg_first = scratch.take<int64_t>(n_seg);
+    int64_t *pairs = scratch.take<int64_t>(n_ptr);
+    uint64_t *keys = scratch.take<uint64_t>(nnz), *vals = scratch.take<uint64_t>(nnz);
+    uint64_t *keys_alt = scratch.take<uint64_t>(nnz), *vals_alt = scratch.take<uint64_t>(nnz);
+    void *tmp = scratch.take<char>(tmp_bytes);
+    if (scratch.used > scratch.cap) {
+        set_error("layout: scratch accounting is off (%zu > %zu)", scratch.used, scratch.cap);
+        return SCHPF_ERR_STATE;
+    }
+    CUDA_TRY(cudaMemsetAsync(unplaced, 0, sizeof(int), stream));
 
     trace_mark(stream, "  alloc");
     // 1. owners ranked by nonzero count, descending (stable: ties keep index order)
-    CUDA_TRY(cudaMemsetAsync(cnt.p, 0, sizeof(int32_t) * n_own, stream));
-    if (nnz > 0) count_owners_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(nnz, d_own, cnt.as<int32_t>());
-    iota_kernel<<<blocks_for(n_own, 256), 256, 0, stream>>>(n_own, ids.as<int32_t>());
-    size_t tmp_bytes = 0, need = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, cnt.as<int32_t>(), cnt_sorted.as<int32_t>(),
-                                                       ids.as<int32_t>(), ids_sorted.as<int32_t>(), (int)n_own,
-                                                       0, 32, stream));
-    tmp_bytes = need;
-    const int key_bits = KEY_LOCAL_BITS + KEY_ROT_BITS + bits_for((uint64_t)(n_seg > 4 ? n_seg / 4 - 1 : 0));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, keys.as<uint64_t>(), keys2.as<uint64_t>(),
-                                             vals.as<uint64_t>(), vals2.as<uint64_t>(), nnz, 0, key_bits, stream));
-    if (need > tmp_bytes) tmp_bytes = need;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, seg_cnt.as<int64_t>(), seg_first.as<int64_t>(), n_seg,
-                                           stream));
-    if (need > tmp_bytes) tmp_bytes = need;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, pairs.as<int64_t>(), L.seg_ptr, n_ptr, stream));
-    if (need > tmp_bytes) tmp_bytes = need;
-    CUDA_TRY(tmp.alloc(tmp_bytes));
-
-    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp.p, tmp_bytes, cnt.as<int32_t>(),
-                                                       cnt_sorted.as<int32_t>(), ids.as<int32_t>(),
-                                                       ids_sorted.as<int32_t>(), (int)n_own, 0, 32, stream));
-    assign_slots_kernel<<<blocks_for(n_slots, 256), 256, 0, stream>>>(n_own, n_slots, ids_sorted.as<int32_t>(),
-                                                                     slot_of.as<int32_t>(), L.own_id);
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * n_own, stream));
+    if (nnz > 0) count_owners_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(nnz, d_own, cnt);
+    iota_kernel<<<blocks_for(n_own, 256), 256, 0, stream>>>(n_own, ids);
+    cub::DoubleBuffer<int32_t> cnt_db(cnt, cnt_alt), ids_db(ids, ids_alt);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, cnt_db, ids_db, (int)n_own, 0, 32, stream));
+    assign_slots_kernel<<<blocks_for(n_slots, 256), 256, 0, stream>>>(n_own, n_slots, ids_db.Current(), slot_of,
+                                                                     L.own_id);
 
     trace_mark(stream, "  owner ranking");
     // 2. sort keys (slot, panel, bank group, local index) and per-list counts
-    CUDA_TRY(cudaMemsetAsync(seg_cnt.p, 0, sizeof(int64_t) * n_seg, stream));
+    CUDA_TRY(cudaMemsetAsync(seg_cnt, 0, sizeof(int64_t) * n_seg, stream));
+    const uint64_t *vals_sorted = vals;
     if (nnz > 0) {
-        make_keys_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(
-            nnz, d_own, d_oth, d_val, slot_of.as<int32_t>(), panel_rows, L.npanel, keys.as<uint64_t>(),
-            vals.as<uint64_t>(), seg_cnt.as<int64_t>());
+        make_keys_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(nnz, d_own, d_oth, d_val, slot_of, panel_rows,
+                                                                  L.npanel, keys, vals, seg_cnt);
         trace_mark(stream, "  keys + counts");
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.as<uint64_t>(), keys2.as<uint64_t>(),
-                                                 vals.as<uint64_t>(), vals2.as<uint64_t>(), nnz, 0, key_bits,
-                                                 stream));
+        // both buffers of a pair are ours, so the sort ping-pongs between them (O(1) extra storage)
+        cub::DoubleBuffer<uint64_t> keys_db(keys, keys_alt), vals_db(vals, vals_alt);
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_db, vals_db, nnz, 0, key_bits, stream));
+        vals_sorted = vals_db.Current();
         trace_mark(stream, "  radix sort");
     }
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, seg_cnt.as<int64_t>(), seg_first.as<int64_t>(), n_seg,
-                                           stream));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, seg_cnt, seg_first, n_seg, stream));
 
     // 3. padded lengths per (warp, panel) and their prefix sum
-    warp_steps_kernel<<<blocks_for(n_ptr, 256), 256, 0, stream>>>(n_warps, L.npanel, seg_cnt.as<int64_t>(),
-                                                                 pairs.as<int64_t>());
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, pairs.as<int64_t>(), L.seg_ptr, n_ptr, stream));
+    warp_steps_kernel<<<blocks_for(n_ptr, 256), 256, 0, stream>>>(n_warps, L.npanel, seg_cnt, pairs);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pairs, L.seg_ptr, n_ptr, stream));
     int64_t total_pairs = 0;
     CUDA_TRY(cudaMemcpyAsync(&total_pairs, L.seg_ptr + (n_ptr - 1), sizeof(int64_t), cudaMemcpyDeviceToHost,
                              stream));
@@ -387,18 +469,16 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
         const int64_t n_qw = n_slots / 4;
         if (packed)
             place_entries_kernel<true><<<blocks_for(n_qw * L.npanel, 128), 128, 0, stream>>>(
-                n_qw, L.npanel, seg_cnt.as<int64_t>(), seg_first.as<int64_t>(), vals2.as<uint64_t>(), L.seg_ptr,
-                L.entries, unplaced.as<int>());
+                n_qw, L.npanel, seg_cnt, seg_first, vals_sorted, L.seg_ptr, L.entries, unplaced);
         else
             place_entries_kernel<false><<<blocks_for(n_qw * L.npanel, 128), 128, 0, stream>>>(
-                n_qw, L.npanel, seg_cnt.as<int64_t>(), seg_first.as<int64_t>(), vals2.as<uint64_t>(), L.seg_ptr,
-                L.entries, unplaced.as<int>());
+                n_qw, L.npanel, seg_cnt, seg_first, vals_sorted, L.seg_ptr, L.entries, unplaced);
     }
     CUDA_TRY(cudaGetLastError());
     trace_mark(stream, "  schedule + place");
     int n_unplaced = 0;
-    CUDA_TRY(cudaMemcpyAsync(&n_unplaced, unplaced.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));   // temporaries are freed on return
+    CUDA_TRY(cudaMemcpyAsync(&n_unplaced, unplaced, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));   // the scratch block is handed back on return
     if (n_unplaced) {
         set_error("layout: %d (quarter warp, panel) schedules left nonzeros unplaced", n_unplaced);
         L.release();

@@ -45,6 +45,9 @@ constexpr int SWEEP_MAX_WARPS = 16;
 #ifndef SWEEP_MINCTA20
 #define SWEEP_MINCTA20 1
 #endif
+#ifndef SWEEP_UNROLL2
+#define SWEEP_UNROLL2 1
+#endif
 
 // A lane keeps 4*KP/2 doubles live (owner row, accumulators, the streamed rows of the two
 // steps in flight) plus ~45 registers of addressing.  One CTA per SM owns the whole shared
@@ -64,6 +67,9 @@ struct SweepCfg {
     static constexpr int D = KP / 2;      // doubles per lane
     static constexpr int MIN_CTAS = sweep_min_ctas(KP);
     static constexpr int MAX_WARPS = sweep_max_warps(KP);
+    // measured on cfg-3 (K=20): 3.36 ms per sweep pair unrolled against 3.50 rolled; above KP=52
+    // the unrolled body spills inside the loop (ptxas -v), so those stay rolled
+    static constexpr bool UNROLL2 = SWEEP_UNROLL2 && KP <= 52;
 };
 
 // two steps of a lane pair as fetched from the entry stream, and their decoded form
@@ -171,12 +177,8 @@ sweep_kernel(const SweepArgs A)
         mbar_wait(mbar, parity);
         parity ^= 1u;
 
-        for (int64_t i = i0; i < i1; ++i) {
-            ep += GROUPS_PER_WARP;
-            Ent nxt2 = nxt;
-            if (i + 2 < i1) nxt2 = Ent::load(A.entries, ep + GROUPS_PER_WARP);
-            const int ex[2] = {cur.row(0), cur.row(1)}, ey[2] = {cur.count(0), cur.count(1)};
-            const bool epad[2] = {cur.pad(0), cur.pad(1)};
+        // the two steps one lane pair takes from one stream element
+        auto process = [&](const int (&ex)[2], const int (&ey)[2], const bool (&epad)[2]) {
             double s[2];
             bool slow = false;
 #if SWEEP_INTERLEAVE
@@ -296,8 +298,42 @@ sweep_kernel(const SweepArgs A)
                 const double v = fma(ym, log(sm), -sm);
                 if (!padm) llh += v;
             }
-            cur = nxt;
-            nxt = nxt2;
+        };
+        if constexpr (Cfg::UNROLL2) {
+            // two stream elements per trip, each in its own registers: no rotation moves, and a
+            // reload is two iterations ahead of its use (cur holds element i, nxt element i + 1)
+            const int64_t eq = q;
+            int64_t i = i0;
+            for (; i + 1 < i1; i += 2) {
+                {
+                    const int ex[2] = {cur.row(0), cur.row(1)}, ey[2] = {cur.count(0), cur.count(1)};
+                    const bool epad[2] = {cur.pad(0), cur.pad(1)};
+                    if (i + 2 < i1) cur = Ent::load(A.entries, (i + 2) * GROUPS_PER_WARP + eq);
+                    process(ex, ey, epad);
+                }
+                {
+                    const int ex[2] = {nxt.row(0), nxt.row(1)}, ey[2] = {nxt.count(0), nxt.count(1)};
+                    const bool epad[2] = {nxt.pad(0), nxt.pad(1)};
+                    if (i + 3 < i1) nxt = Ent::load(A.entries, (i + 3) * GROUPS_PER_WARP + eq);
+                    process(ex, ey, epad);
+                }
+            }
+            if (i < i1) {
+                const int ex[2] = {cur.row(0), cur.row(1)}, ey[2] = {cur.count(0), cur.count(1)};
+                const bool epad[2] = {cur.pad(0), cur.pad(1)};
+                process(ex, ey, epad);
+            }
+        } else {
+            for (int64_t i = i0; i < i1; ++i) {
+                ep += GROUPS_PER_WARP;
+                Ent nxt2 = nxt;
+                if (i + 2 < i1) nxt2 = Ent::load(A.entries, ep + GROUPS_PER_WARP);
+                const int ex[2] = {cur.row(0), cur.row(1)}, ey[2] = {cur.count(0), cur.count(1)};
+                const bool epad[2] = {cur.pad(0), cur.pad(1)};
+                process(ex, ey, epad);
+                cur = nxt;
+                nxt = nxt2;
+            }
         }
         // first entries of the next panel: issued before the barrier so their latency overlaps it
         i0 = n0;
