@@ -100,6 +100,32 @@ __device__ __forceinline__ double div_pos(double y, double s)
     return y * r;
 }
 
+// The same quotient with the product folded into the correction: q = y r, w = q (1 + e + e^2).
+// The dependent chain is seed -> {e, q} -> t -> w, one operation shorter; same error bound.
+__device__ __forceinline__ double div_pos_folded(double y, double s)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+    const double e = fma(-s, r, 1.0);
+    const double q = y * r;
+    const double t = fma(e, e, e);
+    return fma(q, t, q);
+}
+
+// p(lane) + p(lane ^ 1) for every lane, without the shuffle unit: one fp64 m8n8k4 MMA.  A[r][c] is
+// the value of lane 4r + c; with the 0/1 matrix B of the caller (B[c][n] = 1 iff lanes 4r+c and
+// 4r+n/2 form a pair), D[r][2m] -- the first accumulator of lane 4r + m -- is the sum over that
+// lane's own pair.  Adding the two exact zeros changes nothing, so the result equals p + p' bit
+// for bit.  (Finite inputs only: 0 * inf would poison the other pair of the row.)
+__device__ __forceinline__ double pair_sum_mma(double p, double sel)
+{
+    double d0, d1;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(p), "d"(sel), "d"(0.0), "d"(0.0));
+    return d0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);

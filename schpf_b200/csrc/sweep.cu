@@ -48,6 +48,12 @@ constexpr int SWEEP_MAX_WARPS = 16;
 #ifndef SWEEP_UNROLL2
 #define SWEEP_UNROLL2 1
 #endif
+#ifndef SWEEP_DMMA
+#define SWEEP_DMMA 1      // 1: the lane-pair sum of the partial dot products is an fp64 MMA, not shuffles
+#endif
+#ifndef SWEEP_RCP4
+#define SWEEP_RCP4 1      // 1: y/s with the product folded into the Newton step (one dependent op fewer)
+#endif
 
 // A lane keeps 4*KP/2 doubles live (owner row, accumulators, the streamed rows of the two
 // steps in flight) plus ~45 registers of addressing.  One CTA per SM owns the whole shared
@@ -132,6 +138,11 @@ sweep_kernel(const SweepArgs A)
         acc[2 * j + 1] = 0.0;
     }
     double llh = 0.0;
+#if SWEEP_DMMA
+    // B operand of pair_sum_mma: B[c][n] = 1 where column c of A (lane 4r+c) is in the lane pair
+    // that receives D[r][n]; this lane holds B[lane % 4][lane / 4]
+    const double pair_sel = (((lane >> 1) & 1) == (lane >> 4)) ? 1.0 : 0.0;
+#endif
 #if SWEEP_PAD_PRED
     // streamed rows of the step(s) in flight; they persist across iterations so that pad
     // entries can skip their loads and reuse the previous (finite) values with weight 0
@@ -212,14 +223,23 @@ sweep_kernel(const SweepArgs A)
                 }
                 s[e] = s0 + s1;
             }
+#if SWEEP_DMMA
+#pragma unroll
+            for (int e = 0; e < 2; ++e) s[e] = pair_sum_mma(s[e], pair_sel);
+#else
 #pragma unroll
             for (int e = 0; e < 2; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 1);
+#endif
             if (MODE == SWEEP_SHAPE) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const double y = (double)ey[e];
                     const bool ok = s[e] > TINY_NORMALIZER;
+#if SWEEP_RCP4
+                    const double w = ok ? div_pos_folded(y, s[e]) : 0.0;
+#else
                     const double w = ok ? div_pos(y, s[e]) : 0.0;
+#endif
 #pragma unroll
                     for (int k = 0; k < D; ++k) acc[k] = fma(w, bv[e][k], acc[k]);
                     slow |= (!ok && ey[e] != 0);

@@ -48,6 +48,11 @@ def g_minibatch():
     return load_golden("minibatch_small.npz")
 
 
+@pytest.fixture(scope="session")
+def g_fp32():
+    return load_golden("fp32_small.npz")
+
+
 def has_cuda():
     try:
         import torch

@@ -26,6 +26,7 @@ Fixtures
   minibatch_small.npz  scHPF.fit(batchsize=...) (schpf/scHPF_.py:626-631, 642-650, 686-704):
                     A: reinit=True, 240 cells in windows of 64 (wrapping), 9 iterations;
                     B: reinit=False, windows of 100, beta_theta_simultaneous, loss_smoothing=2.
+  fp32_small.npz    the same loop with dtype=np.float32 (mixed precision in the reference).
 """
 import os
 import sys
@@ -198,9 +199,29 @@ def minibatch_small():
     print("minibatch_small: loss A", m.loss, "loss B", base.loss)
 
 
+def fp32_small():
+    """dtype=np.float32 (tests/conftest.py:29 parametrises the reference's tests over it): seeded
+    fp32 init, 10 iterations.  The reference's result is mixed precision."""
+    X = synth_coo(200, 300, 40, 3, seed=5)
+    np.random.seed(31)
+    m = scHPF(3, verbose=False, dtype=np.float32)
+    m._initialize(X)
+    out = dict(row=X.row.astype(np.int32), col=X.col.astype(np.int32),
+               data=X.data.astype(np.int32), shape=np.array(X.shape), seed=31,
+               a=m.a, ap=m.ap, bp=m.bp, c=m.c, cp=m.cp, dp=m.dp)
+    out.update(state_dict(m, "init_"))
+    m.fit(X, reinit=False, min_iter=10, max_iter=10, check_freq=5, verbose=False)
+    out.update(state_dict(m, "fin_"))
+    out["loss"] = np.array(m.loss)
+    out["dtypes"] = np.array([str(getattr(m, n).vi_shape.dtype) + "/" + str(getattr(m, n).vi_rate.dtype)
+                              for n in ("theta", "beta", "xi", "eta")])
+    np.savez_compressed(os.path.join(HERE, "fp32_small.npz"), **out)
+    print("fp32_small: loss", m.loss, out["dtypes"])
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (kernels_k4, cavi_cfg1, reinit_small, simul_small, minibatch_small):
+    for fn in (kernels_k4, cavi_cfg1, reinit_small, simul_small, minibatch_small, fp32_small):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):

@@ -124,6 +124,28 @@ def test_estimator_reinit_and_project_match_seeded_reference(g_reinit, g_cavi, g
     assert_allclose(proj.cell_score(), p["cell_score"], rtol=1e-9)
 
 
+def test_float32_models_keep_their_dtype_and_track_the_reference(g_fp32):
+    """dtype=np.float32: the reference's own result is mixed precision (beta.vi_shape and
+    eta.vi_rate come back fp64); here the arrays are fp32 in and out and the
+    arithmetic is fp64, so the two agree to fp32 rounding (the reference's tests use
+    rtol 1e-5 .. 1e-6 for fp32, tests/test_inference.py:46-121)."""
+    g = g_fp32
+    X = coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(int(v) for v in g["shape"]))
+    np.random.seed(int(g["seed"]))
+    m = scHPF(3, verbose=False, dtype=np.float32)
+    m._initialize(X)
+    for n in ("theta", "beta", "xi", "eta"):
+        assert getattr(m, n).vi_shape.dtype == np.float32
+        assert np.array_equal(getattr(m, n).vi_shape, g["init_%s_shp" % n])     # same fp32 draws
+    m.fit(X, reinit=False, min_iter=10, max_iter=10, check_freq=5)
+    for n in ("theta", "beta", "xi", "eta"):
+        d = getattr(m, n)
+        assert d.vi_shape.dtype == np.float32 and d.vi_rate.dtype == np.float32
+        assert_allclose(d.vi_shape, g["fin_%s_shp" % n], rtol=2e-5)
+        assert_allclose(d.vi_rate, g["fin_%s_rte" % n], rtol=2e-5)
+    assert_allclose(m.loss, g["loss"], rtol=2e-5)
+
+
 def test_simultaneous_matches_reference(g_simul):
     g = _prep_capacity_shapes(g_simul, "init_", 3)
     with _engine_from(g, "init_", 3) as e:

@@ -274,6 +274,28 @@ def test_minibatch_edge_cases(oracle_backend, g_minibatch):
     assert p.beta == m.beta and p.eta == m.eta and len(p.loss) == 3
 
 
+def test_float32_models_keep_their_dtype_and_track_the_reference(oracle_backend, g_fp32):
+    """dtype=np.float32: the reference's own result is mixed precision (beta.vi_shape and
+    eta.vi_rate come back fp64); here the arrays are fp32 in and out and the
+    arithmetic is fp64, so the two agree to fp32 rounding (the reference's tests use
+    rtol 1e-5 .. 1e-6 for fp32, tests/test_inference.py:46-121)."""
+    g = g_fp32
+    X = coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(int(v) for v in g["shape"]))
+    np.random.seed(int(g["seed"]))
+    m = scHPF(3, verbose=False, dtype=np.float32)
+    m._initialize(X)
+    for n in ("theta", "beta", "xi", "eta"):
+        assert getattr(m, n).vi_shape.dtype == np.float32
+        assert np.array_equal(getattr(m, n).vi_shape, g["init_%s_shp" % n])     # same fp32 draws
+    m.fit(X, reinit=False, min_iter=10, max_iter=10, check_freq=5)
+    for n in ("theta", "beta", "xi", "eta"):
+        d = getattr(m, n)
+        assert d.vi_shape.dtype == np.float32 and d.vi_rate.dtype == np.float32
+        assert_allclose(d.vi_shape, g["fin_%s_shp" % n], rtol=2e-5)
+        assert_allclose(d.vi_rate, g["fin_%s_rte" % n], rtol=2e-5)
+    assert_allclose(m.loss, g["loss"], rtol=2e-5)
+
+
 def test_combine_across_cells(g_kernels):
     g = g_kernels
     x = scHPF(4, bp=1.0, dp=2.0, xi=_gam(g, "xi"), theta=_gam(g, "theta"), eta=_gam(g, "eta"), beta=_gam(g, "beta"))
