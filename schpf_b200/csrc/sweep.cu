@@ -39,6 +39,9 @@ constexpr int SWEEP_MAX_WARPS = 16;
 #ifndef SWEEP_W20
 #define SWEEP_W20 16
 #endif
+#ifndef SWEEP_WMID
+#define SWEEP_WMID 12     // warps per CTA for 20 < KP <= 32
+#endif
 #ifndef SWEEP_PAD_PRED
 #define SWEEP_PAD_PRED 0
 #endif
@@ -63,7 +66,7 @@ constexpr int SWEEP_MAX_WARPS = 16;
 __host__ __device__ constexpr int sweep_min_ctas(int KP) { return KP == 20 ? SWEEP_MINCTA20 : 1; }
 __host__ __device__ constexpr int sweep_max_warps(int KP)
 {
-    return KP == 20 ? SWEEP_W20 : KP <= 16 ? 16 : KP <= 32 ? 12 : 8;
+    return KP == 20 ? SWEEP_W20 : KP <= 16 ? 16 : KP <= 32 ? SWEEP_WMID : 8;
 }
 
 template <int KP>
