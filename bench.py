@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--panel-rows", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--target-ctas", type=int, default=0)
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N>1: the engine's all-reduce in order on its stream instead of under the cells-own sweep")
     ap.add_argument("--torch-exchange", action="store_true",
                     help="N>1: all-reduce through torch.distributed instead of the engine's own NCCL call")
     args = ap.parse_args()
@@ -290,7 +292,7 @@ def main():
     nnz_total = int(nnz_t.item())
 
     stream = torch.cuda.current_stream().cuda_stream
-    opts = dict(timing=1, variant=args.variant)
+    opts = dict(timing=1, variant=args.variant, overlap_exchange=0 if args.no_overlap else 1)
     if args.panel_rows:
         opts["panel_rows"] = args.panel_rows
     if args.warps:
@@ -378,7 +380,9 @@ def main():
                                 (info["padded_nnz_cells"] * 8 / 1e9),
                    "parallelism": ("cells sharded over %d GPU(s); one NCCL all-reduce of G*K+K doubles per iteration, %s"
                                    % (world, "torch.distributed" if args.torch_exchange else
-                                      "issued by the engine on its own stream")) if world > 1 else "single GPU",
+                                      "issued by the engine in order on its stream" if args.no_overlap else
+                                      "issued by the engine on a second stream under the cells-own sweep"))
+                   if world > 1 else "single GPU",
                    "variant": "tiled two-pass sweep" if args.variant == 0 else "literal per-nnz atomics",
                    "layout": info, "layout_build_s": layout_s, "bp": bp, "dp": dp},
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
@@ -411,7 +415,8 @@ def main():
         else:
             barrier()
             t0 = time.perf_counter()
-            loc = CaviEngine(C, G, K, device=local_rank, stream=stream, row_offset=rank * C)
+            loc = CaviEngine(C, G, K, device=local_rank, stream=stream, row_offset=rank * C,
+                             overlap_exchange=0 if args.no_overlap else 1)
             loc.set_coo(hrow, hcol, hval)
             loc.set_hyper(HYPER["a"], HYPER["ap"], bp, HYPER["c"], HYPER["cp"], dp)
             loc.set_state(**state)

@@ -116,7 +116,9 @@ int schpf_destroy(schpf_engine_t *h);
  * "target_ctas", "variant" (0 = tiled two-pass sweep, 1 = literal per-nnz
  * kernel with atomics), "timing" (1 = record CUDA events around the sweeps),
  * "packed_entries" (1 = 4-byte stream entries when every count is < 2^19: half the
- * resident layout, slightly slower sweeps) */
+ * resident layout, slightly slower sweeps), "overlap_exchange" (default 1: with an attached
+ * communicator schpf_step runs the all-reduce on a second stream underneath the cells-own sweep;
+ * 0 = in order on the engine's stream) */
 int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value);
 
 /* The sparse count matrix as COO triples (X.row, X.col, X.data of a
@@ -174,8 +176,10 @@ int schpf_step_end(schpf_engine_t *h, int flags);
  * between successive engines) is created from the 128-byte ncclUniqueId that
  * schpf_comm_unique_id produced on rank 0 and the host framework distributed.  After
  * schpf_comm_attach every schpf_step* call of that handle performs the all-reduce
- * (ncclAllReduce, sum, fp64, in place on the exchange buffer) IN ORDER ON THE ENGINE'S OWN
- * STREAM between its two phases, and schpf_loss* returns the loss over all shards.  NCCL is
+ * (ncclAllReduce, sum, fp64, in place on the exchange buffer) between its two phases -- for
+ * schpf_step on a second stream, ordered with events, so that it hides under the cells-own sweep;
+ * for the t == 0 variants in order on the engine's own stream -- and schpf_loss* returns the loss
+ * over all shards.  NCCL is
  * loaded with dlopen("libnccl.so.2") at first use.  Collective calls: every rank must make
  * the same sequence of create / step / loss calls.  The engine does not own the communicator. */
 int schpf_comm_unique_id(char *id128_out);

@@ -162,6 +162,10 @@ struct schpf_engine {
 
     // cell sharding with the exchange done by the engine (schpf_comm_attach; not owned)
     void *comm = nullptr;
+    // the all-reduce runs on its own stream under the cells-own sweep (option "overlap_exchange")
+    int opt_overlap_exchange = 1;
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_folded = nullptr, ev_reduced = nullptr;
 
     // counters
     double n_iterations = 0, n_sweeps = 0, n_launches = 0;
@@ -297,6 +301,44 @@ int zero_accumulators(schpf_engine *h, bool genes_too)
     return SCHPF_OK;
 }
 
+int cells_sweep(schpf_engine *h)
+{
+    // theta side: cells own, gene panels stream through shared memory
+    SweepArgs A = side_args(h, h->cells);
+    A.own_tab = h->Et;
+    A.oth_tab = h->Eb;
+    A.acc = h->acc_t;
+    A.own_elog = h->elog_t;
+    A.oth_elog = h->elog_b;
+    A.direct = h->direct_t;
+    return timed_sweep(h, SWEEP_SHAPE, h->cells, A);
+}
+
+int genes_sweep(schpf_engine *h)
+{
+    // beta side: genes own, cell panels stream
+    SweepArgs B = side_args(h, h->genes);
+    B.own_tab = h->Eb;
+    B.oth_tab = h->Et;
+    B.acc = h->acc_b;
+    B.own_elog = h->elog_b;
+    B.oth_elog = h->elog_t;
+    B.direct = h->direct_b;
+    return timed_sweep(h, SWEEP_SHAPE, h->genes, B);
+}
+
+// this shard's beta shape sums + column sums of theta.e_x (theta BEFORE its update,
+// scHPF_.py:701-703) into the exchange buffer
+int fold_exchange_buffer(schpf_engine *h)
+{
+    const int K = h->K;
+    RC_TRY(launch_fold(h->stream, h->G, K, h->Eb, h->acc_b, h->direct_b, h->exch));
+    CUDA_TRY(cudaMemcpyAsync(h->exch + (size_t)h->G * K, h->colsum_t_next, sizeof(double) * K,
+                             cudaMemcpyDeviceToDevice, h->stream));
+    h->n_launches += 1;
+    return SCHPF_OK;
+}
+
 // mode 0: E-step from the resident state; 1: random phi; 2: Xphi supplied (already scattered by caller)
 int step_begin_impl(schpf_engine *h, int flags, int mode, uint64_t seed)
 {
@@ -314,36 +356,11 @@ int step_begin_impl(schpf_engine *h, int flags, int mode, uint64_t seed)
                                   nullptr, h->direct_t, freeze ? nullptr : h->direct_b));
             h->n_launches += 1;
         } else {
-            // theta side: cells own, gene panels stream through shared memory
-            SweepArgs A = side_args(h, h->cells);
-            A.own_tab = h->Et;
-            A.oth_tab = h->Eb;
-            A.acc = h->acc_t;
-            A.own_elog = h->elog_t;
-            A.oth_elog = h->elog_b;
-            A.direct = h->direct_t;
-            RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->cells, A));
-            if (!freeze) {
-                // beta side: genes own, cell panels stream
-                SweepArgs B = side_args(h, h->genes);
-                B.own_tab = h->Eb;
-                B.oth_tab = h->Et;
-                B.acc = h->acc_b;
-                B.own_elog = h->elog_b;
-                B.oth_elog = h->elog_t;
-                B.direct = h->direct_b;
-                RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->genes, B));
-            }
+            RC_TRY(cells_sweep(h));
+            if (!freeze) RC_TRY(genes_sweep(h));
         }
     }
-    if (!freeze) {
-        // this shard's beta shape sums + column sums of theta.e_x (theta BEFORE its update,
-        // scHPF_.py:701-703) into the exchange buffer
-        RC_TRY(launch_fold(h->stream, h->G, K, h->Eb, h->acc_b, h->direct_b, h->exch));
-        CUDA_TRY(cudaMemcpyAsync(h->exch + (size_t)h->G * K, h->colsum_t_next, sizeof(double) * K,
-                                 cudaMemcpyDeviceToDevice, h->stream));
-        h->n_launches += 1;
-    }
+    if (!freeze) RC_TRY(fold_exchange_buffer(h));
     return SCHPF_OK;
 }
 
@@ -571,6 +588,13 @@ int schpf_destroy(schpf_engine_t *h)
     g_alloc_stream = h->stream;
     cudaStreamSynchronize(h->stream);
     h->comm = nullptr;       // not owned
+    if (h->xstream) {
+        cudaStreamSynchronize(h->xstream);
+        cudaStreamDestroy(h->xstream);
+        cudaEventDestroy(h->ev_folded);
+        cudaEventDestroy(h->ev_reduced);
+        h->xstream = nullptr;
+    }
     free_coo(h);
     dev_free(h->theta_shp); dev_free(h->theta_rte); dev_free(h->beta_shp); dev_free(h->beta_rte);
     dev_free(h->xi_shp); dev_free(h->xi_rte); dev_free(h->eta_shp); dev_free(h->eta_rte);
@@ -599,6 +623,7 @@ int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value)
     else if (!strcmp(key, "timing")) h->opt_timing = (int)value;
     else if (!strcmp(key, "packed_entries")) h->opt_packed_entries = (int)value;
     else if (!strcmp(key, "row_offset")) h->row_offset = value;
+    else if (!strcmp(key, "overlap_exchange")) h->opt_overlap_exchange = (int)value;
     else {
         set_error("unknown option '%s'", key);
         return SCHPF_ERR_ARG;
@@ -737,19 +762,49 @@ int schpf_copy_gene_state(schpf_engine_t *dst, schpf_engine_t *src)
 }
 
 // the one exchange step of an iteration, when the engine owns the communicator
+static int allreduce_exchange(schpf_engine_t *h, cudaStream_t stream)
+{
+    return nccl_check(g_nccl.AllReduce(h->exch, h->exch, (size_t)(h->G * h->K + h->K), NCCL_FLOAT64, NCCL_SUM,
+                                       h->comm, stream),
+                      "ncclAllReduce(exchange buffer)");
+}
+
 static int exchange_if_sharded(schpf_engine_t *h, int flags)
 {
     if (!h->comm || (flags & SCHPF_FREEZE_GENES)) return SCHPF_OK;
-    return nccl_check(g_nccl.AllReduce(h->exch, h->exch, (size_t)(h->G * h->K + h->K), NCCL_FLOAT64, NCCL_SUM,
-                                       h->comm, h->stream),
-                      "ncclAllReduce(exchange buffer)");
+    return allreduce_exchange(h, h->stream);
+}
+
+// One regular iteration on a sharded engine with the all-reduce hidden: the exchange buffer
+// needs only the genes-own sweep, so that sweep goes first and the all-reduce then runs on a
+// second stream underneath the cells-own sweep (1.6 ms of work against a latency-bound 3 MB
+// message).  The two sweeps write different accumulators, so their order does not matter.
+static int step_overlapped(schpf_engine_t *h, int flags)
+{
+    RC_TRY(ensure_tables(h));
+    RC_TRY(zero_accumulators(h, true));
+    RC_TRY(genes_sweep(h));
+    RC_TRY(fold_exchange_buffer(h));
+    CUDA_TRY(cudaEventRecord(h->ev_folded, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->xstream, h->ev_folded, 0));
+    RC_TRY(allreduce_exchange(h, h->xstream));
+    CUDA_TRY(cudaEventRecord(h->ev_reduced, h->xstream));
+    RC_TRY(cells_sweep(h));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_reduced, 0));
+    return step_end_impl(h, flags);
 }
 
 int schpf_step(schpf_engine_t *h, int n_iters, int flags)
 {
     RC_TRY(check_handle(h));
     RC_TRY(require_ready(h));
+    const bool overlap = h->comm && h->xstream && h->opt_overlap_exchange && h->opt_variant == 0 &&
+                         !(flags & SCHPF_FREEZE_GENES);
     for (int t = 0; t < n_iters; ++t) {
+        if (overlap) {
+            RC_TRY(step_overlapped(h, flags));
+            continue;
+        }
         RC_TRY(step_begin_impl(h, flags, 0, 0));
         RC_TRY(exchange_if_sharded(h, flags));
         RC_TRY(step_end_impl(h, flags));
@@ -930,6 +985,11 @@ int schpf_comm_attach(schpf_engine_t *h, void *comm)
 {
     RC_TRY(check_handle(h));
     if (comm) RC_TRY(load_nccl());
+    if (comm && !h->xstream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_folded, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_reduced, cudaEventDisableTiming));
+    }
     h->comm = comm;
     return SCHPF_OK;
 }

@@ -1,7 +1,8 @@
 """Cell sharding on real GPUs (needs >= 2 devices; skipped otherwise): one process per GPU,
-NCCL.  Both transports of schpf_b200.engine.ShardedEngine -- the engine's own in-stream
-ncclAllReduce and torch.distributed.all_reduce on the zero-copy buffer view -- must
-reproduce the unsharded golden run of the reference."""
+NCCL.  All transports of schpf_b200.engine.ShardedEngine -- the engine's own ncclAllReduce
+(overlapped with the cells-own sweep, or in order on its stream) and
+torch.distributed.all_reduce on the zero-copy buffer view -- must reproduce the unsharded
+golden run of the reference."""
 import os
 import socket
 import sys
@@ -30,7 +31,8 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir, native):
+def _worker(rank, world, port, out_dir, mode):
+    native = mode != "torch"
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -45,7 +47,8 @@ def _worker(rank, world, port, out_dir, native):
     b = shard_bounds_by_nnz(np.bincount(g["row"], minlength=C), world)
     lo, hi = int(b[rank]), int(b[rank + 1])
     keep = (g["row"] >= lo) & (g["row"] < hi)
-    local = CaviEngine(hi - lo, G, K, device=rank, row_offset=lo)
+    local = CaviEngine(hi - lo, G, K, device=rank, row_offset=lo,
+                       overlap_exchange=0 if mode == "native-in-stream" else 1)
     local.set_coo(g["row"][keep] - lo, g["col"][keep], g["data"][keep])
     local.set_hyper(*[float(g[k]) for k in ("a", "ap", "bp", "c", "cp", "dp")])
     local.set_state(theta=(g["init_theta_shp"][lo:hi], g["init_theta_rte"][lo:hi]),
@@ -68,11 +71,14 @@ def _worker(rank, world, port, out_dir, native):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("native", [True, False])
-def test_two_gpu_nccl_matches_unsharded(tmp_path, native):
+@pytest.mark.parametrize("mode", ["native-overlapped", "native-in-stream", "torch"])
+def test_two_gpu_nccl_matches_unsharded(tmp_path, mode):
+    """native-overlapped: the engine's all-reduce on a second stream under the cells-own sweep
+    (default); native-in-stream: the same call in order on the engine's stream; torch:
+    torch.distributed.all_reduce on the zero-copy view of the exchange buffer."""
     import torch.multiprocessing as mp
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), native), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
     g = dict(np.load(os.path.join(GOLDEN, "cavi_cfg1.npz")))
     r = [dict(np.load(str(tmp_path / ("rank%d.npz" % k)))) for k in range(world)]
     rel = lambda a, b: float(np.max(np.abs(a - b) / np.abs(b)))
