@@ -108,7 +108,7 @@ def make_problem(torch, device, rank, cfg):
     from schpf_b200.synth import synth_coo_torch
     C, G, K = cfg["cells_per_gpu"], cfg["genes"], cfg["nfactors"]
     row, col, val = synth_coo_torch(C, G, cfg["draws_per_cell"], K, seed=0, device=device,
-                                    row_offset=rank * C)
+                                    row_offset=rank * C, skewed=cfg.get("skewed", False))
     return row, col, val
 
 
@@ -241,6 +241,8 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=4000, help="row prefix timed on the CPU")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--skewed", action="store_true",
+                    help="genes drawn with Gamma(0.5,1) weights instead of uniformly (not the BASELINE workload)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--panel-rows", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
@@ -250,14 +252,16 @@ def main():
     ap.add_argument("--torch-exchange", action="store_true",
                     help="N>1: all-reduce through torch.distributed instead of the engine's own NCCL call")
     args = ap.parse_args()
-    cfg = dict(CFG, cells_per_gpu=args.cells, genes=args.genes, draws_per_cell=args.draws, nfactors=args.factors)
+    cfg = dict(CFG, cells_per_gpu=args.cells, genes=args.genes, draws_per_cell=args.draws, nfactors=args.factors,
+               skewed=args.skewed)
     C, G, K, cf = cfg["cells_per_gpu"], cfg["genes"], cfg["nfactors"], cfg["check_freq"]
     steps, warmup = args.steps, max(args.warmup, 0)
 
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
-    workload = "%dk cells x %dk genes, %d draws/cell, K=%d, fp64%s" % (
-        C // 1000, G // 1000, cfg["draws_per_cell"], K, " per GPU (cells sharded)" if world > 1 else "")
+    workload = "%dk cells x %dk genes, %d draws/cell%s, K=%d, fp64%s" % (
+        C // 1000, G // 1000, cfg["draws_per_cell"], " (skewed gene weights)" if args.skewed else "", K,
+        " per GPU (cells sharded)" if world > 1 else "")
 
     if args.impl == "reference":
         return main_reference(args, cfg, rank, world, workload)

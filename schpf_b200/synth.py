@@ -37,9 +37,11 @@ def synth_coo(ncells, ngenes, nnz_per_cell, nfactors, seed=0, skewed=False):
 
 
 def synth_coo_torch(ncells, ngenes, nnz_per_cell, nfactors, seed=0, device="cuda",
-                    row_offset=0, chunk_cells=8192):
+                    row_offset=0, chunk_cells=8192, skewed=False):
     """Device-side generator; returns (row, col, val) int32 torch tensors on
     ``device``, canonical order (sorted by row then col, no duplicates).
+    ``skewed``: genes drawn with Gamma(0.5, 1) weights (a few genes in most cells, a long
+    tail in few), like ``synth_coo(skewed=True)``.
 
     ``row_offset`` shifts the RNG stream so that shards generated on different
     ranks are independent (rows are returned shard-local, starting at 0).
@@ -61,12 +63,20 @@ def synth_coo_torch(ncells, ngenes, nnz_per_cell, nfactors, seed=0, device="cuda
             torch.manual_seed(int(seed) * 1000003 + 104729 + int(row_offset))
         else:
             torch.cuda.manual_seed(int(seed) * 1000003 + 104729 + int(row_offset))
+        gene_cdf = None
+        if skewed:
+            w = torch._standard_gamma(torch.full((ngenes,), 0.5, device=device, dtype=torch.float64))
+            gene_cdf = torch.cumsum(w / w.sum(), 0)
         rows_out, cols_out, vals_out = [], [], []
         for c0 in range(0, ncells, chunk_cells):
             nc = min(chunk_cells, ncells - c0)
             theta = torch._standard_gamma(torch.full((nc, nfactors), 0.3, device=device,
                                                      dtype=torch.float32))
-            cols = torch.randint(0, ngenes, (nc, nnz_per_cell), device=device, generator=g)
+            if gene_cdf is None:
+                cols = torch.randint(0, ngenes, (nc, nnz_per_cell), device=device, generator=g)
+            else:       # inverse-CDF sampling with replacement; duplicates are merged below
+                u = torch.rand((nc, nnz_per_cell), device=device, dtype=torch.float64, generator=g)
+                cols = torch.searchsorted(gene_cdf, u).clamp_(max=ngenes - 1)
             cols, _ = torch.sort(cols, dim=1)
             keep = torch.ones_like(cols, dtype=torch.bool)
             keep[:, 1:] = cols[:, 1:] != cols[:, :-1]
