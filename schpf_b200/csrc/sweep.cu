@@ -37,7 +37,7 @@ constexpr int SWEEP_MAX_WARPS = 16;
 #define SWEEP_INTERLEAVE 1
 #endif
 #ifndef SWEEP_W20
-#define SWEEP_W20 16
+#define SWEEP_W20 12
 #endif
 #ifndef SWEEP_WMID
 #define SWEEP_WMID 12     // warps per CTA for 20 < KP <= 32
@@ -51,6 +51,9 @@ constexpr int SWEEP_MAX_WARPS = 16;
 #ifndef SWEEP_UNROLL2
 #define SWEEP_UNROLL2 1
 #endif
+#ifndef SWEEP_STEPS4
+#define SWEEP_STEPS4 1    // K=20: four steps (both stream elements of a trip) as one block, 12 warps x 168 registers
+#endif
 #ifndef SWEEP_DMMA
 #define SWEEP_DMMA 1      // 1: the lane-pair sum of the partial dot products is an fp64 MMA, not shuffles
 #endif
@@ -63,6 +66,9 @@ constexpr int SWEEP_MAX_WARPS = 16;
 // memory (the longer the per-owner lists of a panel, the less SELL padding: measured 24 % with
 // 720-row panels, 17 % with 1448), and the CTA is as many warps as the register file allows
 // without spilling (ptxas -v; registers are granted per SM sub-partition, so warps come in 4s).
+// K=20 is the exception that was measured: 12 warps x 168 registers with FOUR steps in flight
+// per lane pair (3.18 ms per sweep pair on cfg-3) beat 16 warps x 128 registers with two (3.29):
+// the kernel is bound by latencies, and 12 x 4 independent steps hide more than 16 x 2.
 __host__ __device__ constexpr int sweep_min_ctas(int KP) { return KP == 20 ? SWEEP_MINCTA20 : 1; }
 __host__ __device__ constexpr int sweep_max_warps(int KP)
 {
@@ -79,7 +85,10 @@ struct SweepCfg {
     // measured on cfg-3 (K=20): 3.36 ms per sweep pair unrolled against 3.50 rolled; above KP=52
     // the unrolled body spills inside the loop (ptxas -v), so those stay rolled
     static constexpr bool UNROLL2 = SWEEP_UNROLL2 && KP <= 52;
+    static constexpr bool STEPS4 = SWEEP_STEPS4 && KP == 20;
 };
+
+template <int N> struct Steps { static constexpr int value = N; };
 
 // two steps of a lane pair as fetched from the entry stream, and their decoded form
 template <bool PACKED> struct EntryPair;
@@ -191,18 +200,19 @@ sweep_kernel(const SweepArgs A)
         mbar_wait(mbar, parity);
         parity ^= 1u;
 
-        // the two steps one lane pair takes from one stream element
-        auto process = [&](const int (&ex)[2], const int (&ey)[2], const bool (&epad)[2]) {
-            double s[2];
+        // the NS steps one lane pair takes from NS/2 stream elements, as one straight-line block
+        auto process = [&](auto ns_tag, const int *ex, const int *ey, const bool *epad) {
+            constexpr int NS = decltype(ns_tag)::value;
+            double s[NS];
             bool slow = false;
 #if SWEEP_INTERLEAVE
             // two steps per iteration as one straight-line block: the two independent dot
             // products / divisions interleave (more ILP, 2*D more live registers)
 #if !SWEEP_PAD_PRED
-            double bv[2][D];
+            double bv[NS][D];
 #endif
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < NS; ++e) {
                 // pad entries (bit 31, count 0) point at a row of a free bank group
                 const uint32_t addr = panel_s + (uint32_t)ex[e] * (ST * 8) + h * 16;
 #pragma unroll
@@ -217,7 +227,7 @@ sweep_kernel(const SweepArgs A)
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < NS; ++e) {
                 double s0 = a[0] * bv[e][0], s1 = a[1] * bv[e][1];
 #pragma unroll
                 for (int k = 2; k < D; k += 2) {
@@ -228,14 +238,14 @@ sweep_kernel(const SweepArgs A)
             }
 #if SWEEP_DMMA
 #pragma unroll
-            for (int e = 0; e < 2; ++e) s[e] = pair_sum_mma(s[e], pair_sel);
+            for (int e = 0; e < NS; ++e) s[e] = pair_sum_mma(s[e], pair_sel);
 #else
 #pragma unroll
-            for (int e = 0; e < 2; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 1);
+            for (int e = 0; e < NS; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 1);
 #endif
             if (MODE == SWEEP_SHAPE) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int e = 0; e < NS; ++e) {
                     const double y = (double)ey[e];
                     const bool ok = s[e] > TINY_NORMALIZER;
 #if SWEEP_RCP4
@@ -250,7 +260,7 @@ sweep_kernel(const SweepArgs A)
             }
 #else
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < NS; ++e) {
 #if SWEEP_PAD_PRED
                 double(&b1)[D] = bv[0];
 #else
@@ -291,7 +301,7 @@ sweep_kernel(const SweepArgs A)
                     // the pair get here together.  Rare: kept rolled, costs the hot path no registers.
                     const int K = A.K;
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
+                    for (int e = 0; e < NS; ++e) {
                         if (s[e] > TINY_NORMALIZER || ey[e] == 0) continue;
                         const double y = (double)ey[e];
                         const double *eo = A.own_elog + (int64_t)own * K;
@@ -315,14 +325,35 @@ sweep_kernel(const SweepArgs A)
             } else {
                 // hpf_numba.py:49-50 without the lgamma term (a constant of the data).  Both lanes of
                 // a pair hold both normalisers: lane 0 finishes step 0, lane 1 step 1 (one log each).
-                const double sm = h ? s[1] : s[0];
-                const bool padm = h ? epad[1] : epad[0];
-                const double ym = (double)(h ? ey[1] : ey[0]);
-                const double v = fma(ym, log(sm), -sm);
-                if (!padm) llh += v;
+#pragma unroll
+                for (int e2 = 0; e2 < NS; e2 += 2) {
+                    const double sm = h ? s[e2 + 1] : s[e2];
+                    const bool padm = h ? epad[e2 + 1] : epad[e2];
+                    const double ym = (double)(h ? ey[e2 + 1] : ey[e2]);
+                    const double v = fma(ym, log(sm), -sm);
+                    if (!padm) llh += v;
+                }
             }
         };
-        if constexpr (Cfg::UNROLL2) {
+        if constexpr (Cfg::STEPS4) {
+            // both stream elements of a trip as ONE block of four steps: twice the independent
+            // work per warp (fewer warps fit: 4 * D more live registers)
+            const int64_t eq = q;
+            int64_t i = i0;
+            for (; i + 1 < i1; i += 2) {
+                const int ex[4] = {cur.row(0), cur.row(1), nxt.row(0), nxt.row(1)};
+                const int ey[4] = {cur.count(0), cur.count(1), nxt.count(0), nxt.count(1)};
+                const bool epad[4] = {cur.pad(0), cur.pad(1), nxt.pad(0), nxt.pad(1)};
+                if (i + 2 < i1) cur = Ent::load(A.entries, (i + 2) * GROUPS_PER_WARP + eq);
+                if (i + 3 < i1) nxt = Ent::load(A.entries, (i + 3) * GROUPS_PER_WARP + eq);
+                process(Steps<4>{}, ex, ey, epad);
+            }
+            if (i < i1) {
+                const int ex[2] = {cur.row(0), cur.row(1)}, ey[2] = {cur.count(0), cur.count(1)};
+                const bool epad[2] = {cur.pad(0), cur.pad(1)};
+                process(Steps<2>{}, ex, ey, epad);
+            }
+        } else if constexpr (Cfg::UNROLL2) {
             // two stream elements per trip, each in its own registers: no rotation moves, and a
             // reload is two iterations ahead of its use (cur holds element i, nxt element i + 1)
             const int64_t eq = q;
@@ -332,19 +363,19 @@ sweep_kernel(const SweepArgs A)
                     const int ex[2] = {cur.row(0), cur.row(1)}, ey[2] = {cur.count(0), cur.count(1)};
                     const bool epad[2] = {cur.pad(0), cur.pad(1)};
                     if (i + 2 < i1) cur = Ent::load(A.entries, (i + 2) * GROUPS_PER_WARP + eq);
-                    process(ex, ey, epad);
+                    process(Steps<2>{}, ex, ey, epad);
                 }
                 {
                     const int ex[2] = {nxt.row(0), nxt.row(1)}, ey[2] = {nxt.count(0), nxt.count(1)};
                     const bool epad[2] = {nxt.pad(0), nxt.pad(1)};
                     if (i + 3 < i1) nxt = Ent::load(A.entries, (i + 3) * GROUPS_PER_WARP + eq);
-                    process(ex, ey, epad);
+                    process(Steps<2>{}, ex, ey, epad);
                 }
             }
             if (i < i1) {
                 const int ex[2] = {cur.row(0), cur.row(1)}, ey[2] = {cur.count(0), cur.count(1)};
                 const bool epad[2] = {cur.pad(0), cur.pad(1)};
-                process(ex, ey, epad);
+                process(Steps<2>{}, ex, ey, epad);
             }
         } else {
             for (int64_t i = i0; i < i1; ++i) {
@@ -353,7 +384,7 @@ sweep_kernel(const SweepArgs A)
                 if (i + 2 < i1) nxt2 = Ent::load(A.entries, ep + GROUPS_PER_WARP);
                 const int ex[2] = {cur.row(0), cur.row(1)}, ey[2] = {cur.count(0), cur.count(1)};
                 const bool epad[2] = {cur.pad(0), cur.pad(1)};
-                process(ex, ey, epad);
+                process(Steps<2>{}, ex, ey, epad);
                 cur = nxt;
                 nxt = nxt2;
             }
