@@ -175,18 +175,6 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
     return v;
 }
 
-// The same, predicated on `word >= 0` (pad entries have bit 31 set): a pad issues no
-// load at all -- no wavefront, no bank conflict -- and leaves x, y as they were.
-__device__ __forceinline__ void lds_f64x2_unless_pad(double &x, double &y, uint32_t addr, int word)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ge.s32 p, %3, 0;\n\t"
-        "@p ld.shared.v2.f64 {%0, %1}, [%2];\n\t}"
-        : "+d"(x), "+d"(y)
-        : "r"(addr), "r"(word));
-}
-
 // streaming 128-bit load that does not allocate in L1 (entry stream is read once)
 __device__ __forceinline__ int4 ld_stream_int4(const int4 *p)
 {

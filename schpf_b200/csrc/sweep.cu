@@ -23,7 +23,12 @@
 // holds the 16-byte units {2j+h} of the K-row), walks a range of panels of the
 // other axis; each panel is brought into shared memory with one 1-D bulk
 // async copy (cp.async.bulk -> UBLKCP) completing on an mbarrier; the entry
-// stream is a per-(warp, panel) sliced-ELL block, two steps per 128-bit load.
+// stream is a per-(warp, panel) sliced-ELL block, two steps per 128-bit load.  A loop trip takes
+// two stream elements (four steps) from two register sets that are reloaded a whole trip ahead
+// of their use; at K=20 the four steps are one straight-line block (12-warp CTAs), otherwise two
+// blocks of two (as many warps as the registers allow).  The two lanes' partial dot products
+// are summed by an fp64 MMA against a 0/1 matrix (DMMA.8x8x4) rather than by shuffles, which
+// keeps that traffic off the shared-memory pipe the row loads saturate.
 #include "common.cuh"
 
 namespace schpf {
@@ -41,9 +46,6 @@ constexpr int SWEEP_MAX_WARPS = 16;
 #endif
 #ifndef SWEEP_WMID
 #define SWEEP_WMID 12     // warps per CTA for 20 < KP <= 32
-#endif
-#ifndef SWEEP_PAD_PRED
-#define SWEEP_PAD_PRED 0
 #endif
 #ifndef SWEEP_MINCTA20
 #define SWEEP_MINCTA20 1
@@ -155,13 +157,6 @@ sweep_kernel(const SweepArgs A)
     // that receives D[r][n]; this lane holds B[lane % 4][lane / 4]
     const double pair_sel = (((lane >> 1) & 1) == (lane >> 4)) ? 1.0 : 0.0;
 #endif
-#if SWEEP_PAD_PRED
-    // streamed rows of the step(s) in flight; they persist across iterations so that pad
-    // entries can skip their loads and reuse the previous (finite) values with weight 0
-    double bv[SWEEP_INTERLEAVE ? 2 : 1][D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) bv[0][k] = bv[SWEEP_INTERLEAVE ? 1 : 0][k] = 0.0;
-#endif
 
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -208,22 +203,16 @@ sweep_kernel(const SweepArgs A)
 #if SWEEP_INTERLEAVE
             // two steps per iteration as one straight-line block: the two independent dot
             // products / divisions interleave (more ILP, 2*D more live registers)
-#if !SWEEP_PAD_PRED
             double bv[NS][D];
-#endif
 #pragma unroll
             for (int e = 0; e < NS; ++e) {
                 // pad entries (bit 31, count 0) point at a row of a free bank group
                 const uint32_t addr = panel_s + (uint32_t)ex[e] * (ST * 8) + h * 16;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
-#if SWEEP_PAD_PRED
-                    lds_f64x2_unless_pad(bv[e][2 * j], bv[e][2 * j + 1], addr + j * 32, ex[e]);
-#else
                     const double2 v = lds_f64x2(addr + j * 32);
                     bv[e][2 * j] = v.x;
                     bv[e][2 * j + 1] = v.y;
-#endif
                 }
             }
 #pragma unroll
@@ -261,21 +250,13 @@ sweep_kernel(const SweepArgs A)
 #else
 #pragma unroll
             for (int e = 0; e < NS; ++e) {
-#if SWEEP_PAD_PRED
-                double(&b1)[D] = bv[0];
-#else
                 double b1[D];
-#endif
                 const uint32_t addr = panel_s + (uint32_t)ex[e] * (ST * 8) + h * 16;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
-#if SWEEP_PAD_PRED
-                    lds_f64x2_unless_pad(b1[2 * j], b1[2 * j + 1], addr + j * 32, ex[e]);
-#else
                     const double2 v = lds_f64x2(addr + j * 32);
                     b1[2 * j] = v.x;
                     b1[2 * j + 1] = v.y;
-#endif
                 }
                 double s0 = a[0] * b1[0], s1 = a[1] * b1[1];
 #pragma unroll
