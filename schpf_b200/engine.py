@@ -239,6 +239,22 @@ def shard_bounds_by_nnz(row_counts, world_size):
     return np.asarray(bounds, dtype=np.int64)
 
 
+def shard_coo_rows(X, rank, world_size):
+    """This rank's share of a cells x genes matrix for a cell-sharded fit: the contiguous,
+    nnz-balanced range of rows `shard_bounds_by_nnz` assigns to `rank`, re-based to start at 0.
+
+    Returns (X_local: coo_matrix of shape (hi - lo, ngenes), lo, hi).  Every rank must call it
+    on the same matrix (or on a matrix with the same per-cell counts)."""
+    from scipy.sparse import coo_matrix
+    X = X.tocoo()
+    bounds = shard_bounds_by_nnz(np.bincount(X.row, minlength=X.shape[0]), world_size)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    keep = (X.row >= lo) & (X.row < hi)
+    local = coo_matrix((X.data[keep], (X.row[keep] - lo, X.col[keep])), shape=(hi - lo, X.shape[1]),
+                       dtype=X.dtype)
+    return local, lo, hi
+
+
 class ShardedEngine(object):
     """Cells sharded over the ranks of a torch.distributed process group.
 

@@ -67,6 +67,23 @@ def _replicate_from_rank0(group, *gammas):
     return out
 
 
+def _all_gather_rows(group, arr):
+    """Rows of every rank's `arr` (same trailing shape, different row counts) in rank order."""
+    import torch
+    import torch.distributed as dist
+    dev, world = _dist_device(group), dist.get_world_size(group)
+    n = torch.tensor([arr.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    padded = np.zeros((max(counts),) + arr.shape[1:], dtype=np.float64)
+    padded[:arr.shape[0]] = arr
+    mine = torch.as_tensor(padded).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)]).astype(arr.dtype, copy=False)
+
+
 def _shared_seed(group):
     """One random-phi seed for all ranks, drawn from rank 0's numpy stream."""
     import torch.distributed as dist
@@ -282,6 +299,17 @@ class scHPF(BaseEstimator):
         """sklearn-convention alias: cell scores of `X` projected onto this model
         (the reference has no `transform`)."""
         return self.project(X, replace=False, **kwargs).cell_score()
+
+    def gather_cells(self, process_group=None):
+        """After a cell-sharded `fit(X_shard, process_group=...)`: a copy of this model whose
+        xi / theta hold the cells of ALL ranks in rank order (collective; every rank gets it).
+        Genes, hyperparameters and the loss are already the same everywhere."""
+        full = deepcopy(self)
+        full.xi = HPF_Gamma(_all_gather_rows(process_group, self.xi.vi_shape),
+                            _all_gather_rows(process_group, self.xi.vi_rate))
+        full.theta = HPF_Gamma(_all_gather_rows(process_group, self.theta.vi_shape),
+                               _all_gather_rows(process_group, self.theta.vi_rate))
+        return full
 
     def fit_transform(self, X, y=None, **kwargs):
         return self.fit(X, **kwargs).cell_score()

@@ -97,7 +97,7 @@ def _estimator_worker(rank, world, port, out_dir):
     from scipy.sparse import coo_matrix
     from schpf_b200 import scHPF, HPF_Gamma
     from schpf_b200 import scHPF_ as shell
-    from schpf_b200.engine import shard_bounds_by_nnz
+    from schpf_b200.engine import shard_coo_rows
     from oracle_engine import OracleEngine
     shell._engine_factory = OracleEngine               # host logic under test, arithmetic from the oracle
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -105,10 +105,8 @@ def _estimator_worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = dict(np.load(os.path.join(GOLDEN, "cavi_cfg1.npz")))
     C, G = (int(v) for v in g["shape"])
-    b = shard_bounds_by_nnz(np.bincount(g["row"], minlength=C), world)
-    lo, hi = int(b[rank]), int(b[rank + 1])
-    keep = (g["row"] >= lo) & (g["row"] < hi)
-    X = coo_matrix((g["data"][keep], (g["row"][keep] - lo, g["col"][keep])), shape=(hi - lo, G))
+    X, lo, hi = shard_coo_rows(coo_matrix((g["data"], (g["row"], g["col"])), shape=(C, G)), rank, world)
+    assert X.shape == (hi - lo, G)
     gam = lambda n, sl: HPF_Gamma(g["init_" + n + "_shp"][sl].copy(), g["init_" + n + "_rte"][sl].copy())
     # rank 1 is handed garbage for the gene side: it must end up with rank 0's
     scale = 1.0 if rank == 0 else 3.0
@@ -116,8 +114,11 @@ def _estimator_worker(rank, world, port, out_dir):
     eta = HPF_Gamma(g["init_eta_shp"] * scale, g["init_eta_rte"] * scale)
     m = scHPF(5, verbose=False, xi=gam("xi", slice(lo, hi)), theta=gam("theta", slice(lo, hi)), eta=eta, beta=beta)
     m.fit(X, reinit=False, min_iter=10, max_iter=10, check_freq=3, process_group=dist.group.WORLD)
+    full = m.gather_cells(dist.group.WORLD)
+    assert full.ncells == C and m.ncells == hi - lo and full.beta == m.beta
     np.savez(os.path.join(out_dir, "est%d.npz" % rank), lo=lo, hi=hi, bp=m.bp, dp=m.dp, loss=np.array(m.loss),
-             theta_shp=m.theta.vi_shape, xi_rte=m.xi.vi_rate, beta_shp=m.beta.vi_shape, eta_rte=m.eta.vi_rate)
+             theta_shp=m.theta.vi_shape, xi_rte=m.xi.vi_rate, beta_shp=m.beta.vi_shape, eta_rte=m.eta.vi_rate,
+             full_theta_shp=full.theta.vi_shape, full_xi_rte=full.xi.vi_rate)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -139,3 +140,7 @@ def test_estimator_fit_with_process_group(tmp_path):
     assert rel(np.concatenate([r[0]["theta_shp"], r[1]["theta_shp"]]), g["it10_theta_shp"]) < 1e-10
     assert rel(np.concatenate([r[0]["xi_rte"], r[1]["xi_rte"]]), g["it10_xi_rte"]) < 1e-10
     assert np.allclose(r[0]["loss"], g["it10_loss"], rtol=1e-10)
+    # gather_cells: every rank ends up with all cells, in rank order
+    for k in range(world):
+        assert np.array_equal(r[k]["full_theta_shp"], np.concatenate([r[0]["theta_shp"], r[1]["theta_shp"]]))
+        assert np.array_equal(r[k]["full_xi_rte"], np.concatenate([r[0]["xi_rte"], r[1]["xi_rte"]]))
