@@ -150,6 +150,12 @@ int schpf_get_state(schpf_engine_t *h,
  * the same device with the same ngenes / nfactors.  This is how the minibatch loop (scHPF_.py:642-650:
  * a different row subset of X every iteration) hands the gene side from one batch's engine to the next. */
 int schpf_copy_gene_state(schpf_engine_t *dst, schpf_engine_t *src);
+/* Copy theta (shape, rate rows) and xi (shape, rate) of `nrows` cells, src rows [src_row0, +nrows) ->
+ * dst rows [dst_row0, +nrows), device to device.  Same device and nfactors.  With the cells of a
+ * matrix permuted once by the minibatch shuffle (util.py:220-221) every batch is a contiguous row
+ * range, and this moves a batch between the engine that holds all cells and the batch's engine. */
+int schpf_copy_cell_state(schpf_engine_t *dst, int64_t dst_row0, schpf_engine_t *src, int64_t src_row0,
+                          int64_t nrows);
 
 /* n full CAVI iterations (Xphi -> beta -> eta -> theta -> xi), single GPU. */
 int schpf_step(schpf_engine_t *h, int n_iters, int flags);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "schpf_set_state": [c_vp] + [c_vp] * 8,
     "schpf_get_state": [c_vp] + [c_vp] * 8,
     "schpf_copy_gene_state": [c_vp, c_vp],
+    "schpf_copy_cell_state": [c_vp, c_i64, c_vp, c_i64, c_i64],
     "schpf_step": [c_vp, c_int, c_int],
     "schpf_step_with_xphi": [c_vp, p_dbl, c_int],
     "schpf_step_random_phi": [c_vp, c_u64, c_int],

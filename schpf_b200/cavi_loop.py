@@ -20,19 +20,46 @@ HOST_DIRICHLET_LIMIT = 1 << 24
 # distinct windows is at most this; beyond, one engine is re-laid out every iteration
 MINIBATCH_ENGINE_CACHE = 64
 
+# theta / xi of all cells on the device between minibatch iterations (see MinibatchLoop).
+# Opt-in: the host logic is covered by the CPU tests, the copies have not run on hardware yet.
+MINIBATCH_DEVICE_STATE = False
 
-def minibatch_windows(ncells, batchsize):
+
+class MinibatchSchedule(object):
     """The reference's batch schedule (schpf/util.py:218-231): ONE `np.random.shuffle` of the
     cell order at the first draw, then consecutive windows of `batchsize` cells that wrap
-    around the end.  Yields (window start, cell indices)."""
-    assert ncells >= batchsize
-    order = np.arange(ncells)
-    np.random.shuffle(order)
-    offsets = np.arange(batchsize)
-    start = 0
+    around the end.  `next()` returns (window start, cell indices); `order` is the shuffled
+    cell order (None until the first draw, like the reference's lazy generator)."""
+
+    def __init__(self, ncells, batchsize):
+        assert ncells >= batchsize
+        self.ncells, self.batchsize = int(ncells), int(batchsize)
+        self.order, self._start = None, 0
+        self._offsets = np.arange(self.batchsize)
+
+    def draw_order(self):
+        if self.order is None:
+            self.order = np.arange(self.ncells)
+            np.random.shuffle(self.order)
+        return self.order
+
+    def next(self):
+        order, start = self.draw_order(), self._start
+        self._start = (start + self.batchsize) % self.ncells
+        return start, order[(start + self._offsets) % self.ncells]
+
+    def pieces(self, start):
+        """The window starting at `start` as contiguous ranges of the shuffled order:
+        [(first position, length)], two entries when it wraps."""
+        n1 = min(self.batchsize, self.ncells - start)
+        return [(start, n1)] + ([(0, self.batchsize - n1)] if n1 < self.batchsize else [])
+
+
+def minibatch_windows(ncells, batchsize):
+    """Generator form of MinibatchSchedule: yields (window start, cell indices)."""
+    sched = MinibatchSchedule(ncells, batchsize)
     while True:
-        yield start, order[(start + offsets) % ncells]
-        start = (start + batchsize) % ncells
+        yield sched.next()
 
 
 def _random_phi_step(engine, data, nfactors, **flags):
@@ -100,40 +127,73 @@ class MinibatchLoop(object):
     over the batch's rows (re-based to 0..batchsize-1, all genes): its sweeps and
     finalisations are the full-batch kernels, in the `batched` order of scHPF_.py:686-704
     (theta/xi first, then beta from the same Xphi with the NEW theta in its rate;
-    SCHPF_CELLS_FIRST).  theta/xi of all cells live on the host between iterations (a batch
-    moves 4*batchsize*K doubles); beta/eta stay on the device and are handed from one
-    batch's engine to the next device-to-device.  The batch schedule is a fixed cyclic
-    sequence of windows over one shuffled cell order, so while there are few distinct
-    windows each keeps its engine and device layout; otherwise one engine is re-laid out
-    every iteration.  The loss is taken by a full-matrix engine that is only built if the
-    default loss is used.
+    SCHPF_CELLS_FIRST).  beta/eta stay on the device and are handed from one batch's engine
+    to the next device-to-device.  The batch schedule is a fixed cyclic sequence of windows
+    over one shuffled cell order, so while there are few distinct windows each keeps its
+    engine and device layout; otherwise one engine is re-laid out every iteration.
+
+    Where theta/xi of all cells live between iterations:
+      host (default)   numpy arrays; a batch moves 4*batchsize*K doubles over PCIe and the loop
+                       synchronises twice per iteration;
+      device (`device_state=True`, opt-in until it has run on hardware) the cells are permuted
+                       ONCE by the shuffle, so every window is a contiguous row range (two when it
+                       wraps) of a full-size "master" engine, and a batch moves with
+                       `schpf_copy_cell_state` (D2D, no host synchronisation in the loop).
+    The default loss is taken by a full-matrix engine (the master in device mode) that gets
+    its layout only if that loss is used.
     """
 
-    def __init__(self, new_engine, X, hyper, state, nfactors, batchsize, freeze_genes, simultaneous):
+    def __init__(self, new_engine, X, hyper, state, nfactors, batchsize, freeze_genes, simultaneous,
+                 device_state=None):
         self.new_engine, self.hyper, self.nfactors = new_engine, hyper, nfactors
         self.ncells, self.ngenes = X.shape
         self.batchsize = int(batchsize)
         self.freeze_genes = freeze_genes
         self.flags = dict(freeze_genes=freeze_genes, simultaneous=simultaneous, cells_first=True)
+        self.device_state = MINIBATCH_DEVICE_STATE if device_state is None else bool(device_state)
         self.X = X
         # like the reference's X.tocsr(): duplicates summed, columns sorted within a row
         self.Xcsr = X.tocsr()
         f = lambda pair: [np.array(pair[0], dtype=np.float64, copy=True), np.array(pair[1], dtype=np.float64, copy=True)]
-        self.theta, self.xi = f(state["theta"]), f(state["xi"])
+        self.theta, self.xi = f(state["theta"]), f(state["xi"])      # host mode: the live copy
         self._gene_init = dict(beta=state["beta"], eta=state["eta"])
-        self.windows = minibatch_windows(self.ncells, self.batchsize)
+        self.schedule = MinibatchSchedule(self.ncells, self.batchsize)
         n_windows = self.ncells // gcd(self.ncells, self.batchsize)
         self.cache_engines = n_windows <= MINIBATCH_ENGINE_CACHE
         self.engines = {}          # window start -> engine (only one entry when not caching)
         self.current = None        # the engine holding the newest beta / eta
-        self.full = None
+        self.full = None           # full-matrix engine: loss; in device mode also all cells' theta / xi
+        self.full_has_coo = False
+        self.Xp_csr = None         # device mode: rows in shuffled order
 
     # -- engines -------------------------------------------------------------
+    def _full_engine(self, with_coo):
+        if self.full is None:
+            self.full = self.new_engine(self.ncells, self.ngenes)
+            self.full.set_hyper(*self.hyper)
+            if self.device_state:
+                order = self.schedule.draw_order()
+                self.Xp_csr = self.Xcsr[order, :]
+                self.full.set_state(theta=(self.theta[0][order], self.theta[1][order]),
+                                    xi=(self.xi[0][order], self.xi[1][order]), **self._gene_init)
+        if with_coo and not self.full_has_coo:
+            Xf = self.Xp_csr.tocoo() if self.device_state else self.X
+            self.full.set_coo(Xf.row, Xf.col, Xf.data)
+            self.full_has_coo = True
+        return self.full
+
+    def _batch_coo(self, start, batch_ix):
+        if self.device_state:       # the same rows in the same order, sliced from the permuted matrix
+            from scipy.sparse import vstack
+            parts = [self.Xp_csr[a:a + n, :] for a, n in self.schedule.pieces(start)]
+            return (parts[0] if len(parts) == 1 else vstack(parts, format="csr")).tocoo()
+        return self.Xcsr[batch_ix, :].tocoo()
+
     def _batch_engine(self, start, batch_ix):
         key = start if self.cache_engines else 0
         eng, Xb = self.engines.get(key), None
         if eng is None or not self.cache_engines:
-            Xb = self.Xcsr[batch_ix, :].tocoo()
+            Xb = self._batch_coo(start, batch_ix)
             if eng is None:
                 eng = self.new_engine(self.batchsize, self.ngenes)
                 eng.set_hyper(*self.hyper)
@@ -147,40 +207,63 @@ class MinibatchLoop(object):
 
     def run(self, t, n, reinit):
         for tt in range(t, t + n):
-            start, batch_ix = next(self.windows)
+            start, batch_ix = self.schedule.next()
+            if self.device_state:
+                master = self._full_engine(with_coo=False)
             eng, Xb = self._batch_engine(start, batch_ix)
-            eng.set_state(theta=(self.theta[0][batch_ix], self.theta[1][batch_ix]),
-                          xi=(self.xi[0][batch_ix], self.xi[1][batch_ix]))
+            if self.device_state:
+                at = 0
+                for a, m in self.schedule.pieces(start):
+                    eng.copy_cell_state_from(master, at, a, m)
+                    at += m
+            else:
+                eng.set_state(theta=(self.theta[0][batch_ix], self.theta[1][batch_ix]),
+                              xi=(self.xi[0][batch_ix], self.xi[1][batch_ix]))
             if tt == 0 and reinit:
                 if Xb is None:
-                    Xb = self.Xcsr[batch_ix, :].tocoo()
+                    Xb = self._batch_coo(start, batch_ix)
                 _random_phi_step(eng, Xb.data, self.nfactors, **self.flags)
             else:
                 eng.step(1, **self.flags)
-            st = eng.get_state(("theta", "xi"))
-            for k in (0, 1):
-                self.theta[k][batch_ix] = st["theta"][k]
-                self.xi[k][batch_ix] = st["xi"][k]
+            if self.device_state:
+                at = 0
+                for a, m in self.schedule.pieces(start):
+                    master.copy_cell_state_from(eng, a, at, m)
+                    at += m
+            else:
+                st = eng.get_state(("theta", "xi"))
+                for k in (0, 1):
+                    self.theta[k][batch_ix] = st["theta"][k]
+                    self.xi[k][batch_ix] = st["xi"][k]
             self.current = eng
 
     # -- read-outs -------------------------------------------------------------
     def loss(self):
         """mean negative Poisson llh of ALL of X (the reference's default loss is bound to the
         whole training matrix, scHPF_.py:622-624) under the current state."""
-        if self.full is None:
-            self.full = self.new_engine(self.ncells, self.ngenes)
-            self.full.set_hyper(*self.hyper)
-            self.full.set_coo(self.X.row, self.X.col, self.X.data)
-        self.full.set_state(theta=tuple(self.theta), xi=tuple(self.xi))
+        full = self._full_engine(with_coo=True)
+        if not self.device_state:
+            full.set_state(theta=tuple(self.theta), xi=tuple(self.xi))
         if self.current is None:
-            self.full.set_state(**self._gene_init)
+            full.set_state(**self._gene_init)
         else:
-            self.full.copy_gene_state_from(self.current)
-        return self.full.loss()
+            full.copy_gene_state_from(self.current)
+        return full.loss()
 
     def host_state(self):
-        out = {"theta": (self.theta[0].copy(), self.theta[1].copy()),
-               "xi": (self.xi[0].copy(), self.xi[1].copy())}
+        if self.device_state and self.full is not None:
+            st, order = self.full.get_state(("theta", "xi")), self.schedule.order
+            out = {}
+            for name in ("theta", "xi"):        # back from the shuffled to the caller's cell order
+                pair = []
+                for arr in st[name]:
+                    back = np.empty_like(arr)
+                    back[order] = arr
+                    pair.append(back)
+                out[name] = tuple(pair)
+        else:
+            out = {"theta": (self.theta[0].copy(), self.theta[1].copy()),
+                   "xi": (self.xi[0].copy(), self.xi[1].copy())}
         if not self.freeze_genes:
             if self.current is None:
                 out.update({k: (np.array(v[0], dtype=np.float64), np.array(v[1], dtype=np.float64))

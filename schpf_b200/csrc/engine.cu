@@ -749,15 +749,57 @@ int schpf_copy_gene_state(schpf_engine_t *dst, schpf_engine_t *src)
         set_error("schpf_copy_gene_state: source engine has no state");
         return SCHPF_ERR_STATE;
     }
-    // the two handles may use different streams: finish the source's work first
-    CUDA_TRY(cudaStreamSynchronize(src->stream));
+    // the two handles may use different streams: then finish the source's work first
+    const bool two_streams = dst->stream != src->stream;
+    if (two_streams) CUDA_TRY(cudaStreamSynchronize(src->stream));
     const size_t GK = sizeof(double) * (size_t)dst->G * dst->K, Gb = sizeof(double) * (size_t)dst->G;
     CUDA_TRY(cudaMemcpyAsync(dst->beta_shp, src->beta_shp, GK, cudaMemcpyDeviceToDevice, dst->stream));
     CUDA_TRY(cudaMemcpyAsync(dst->beta_rte, src->beta_rte, GK, cudaMemcpyDeviceToDevice, dst->stream));
     CUDA_TRY(cudaMemcpyAsync(dst->eta_shp, src->eta_shp, Gb, cudaMemcpyDeviceToDevice, dst->stream));
     CUDA_TRY(cudaMemcpyAsync(dst->eta_rte, src->eta_rte, Gb, cudaMemcpyDeviceToDevice, dst->stream));
-    CUDA_TRY(cudaStreamSynchronize(dst->stream));   // src may be stepped again right away
+    if (two_streams) CUDA_TRY(cudaStreamSynchronize(dst->stream));   // src may be stepped again right away
     dst->tables_b_valid = false;
+    return SCHPF_OK;
+}
+
+int schpf_copy_cell_state(schpf_engine_t *dst, int64_t dst_row0, schpf_engine_t *src, int64_t src_row0,
+                          int64_t nrows)
+{
+    RC_TRY(check_handle(src));
+    RC_TRY(check_handle(dst));
+    if (dst->device != src->device || dst->K != src->K) {
+        set_error("schpf_copy_cell_state: handles differ (device %d/%d, nfactors %d/%d)", dst->device,
+                  src->device, dst->K, src->K);
+        return SCHPF_ERR_ARG;
+    }
+    if (nrows < 0 || dst_row0 < 0 || src_row0 < 0 || dst_row0 + nrows > dst->C || src_row0 + nrows > src->C) {
+        set_error("schpf_copy_cell_state: rows [%lld, +%lld) of %lld -> [%lld, +%lld) of %lld out of range",
+                  (long long)src_row0, (long long)nrows, (long long)src->C, (long long)dst_row0,
+                  (long long)nrows, (long long)dst->C);
+        return SCHPF_ERR_ARG;
+    }
+    if (dst == src && dst_row0 == src_row0) return SCHPF_OK;
+    if (dst == src && dst_row0 < src_row0 + nrows && src_row0 < dst_row0 + nrows) {
+        set_error("schpf_copy_cell_state: overlapping ranges within one handle");
+        return SCHPF_ERR_ARG;
+    }
+    if (!src->have_state) {
+        set_error("schpf_copy_cell_state: source engine has no state");
+        return SCHPF_ERR_STATE;
+    }
+    if (nrows == 0) return SCHPF_OK;
+    const bool two_streams = dst->stream != src->stream;
+    if (two_streams) CUDA_TRY(cudaStreamSynchronize(src->stream));     // the source's work first
+    const size_t K = (size_t)dst->K;
+    const size_t rowsK = sizeof(double) * (size_t)nrows * K, rows1 = sizeof(double) * (size_t)nrows;
+    const size_t d0 = (size_t)dst_row0, s0 = (size_t)src_row0;
+    CUDA_TRY(cudaMemcpyAsync(dst->theta_shp + d0 * K, src->theta_shp + s0 * K, rowsK, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->theta_rte + d0 * K, src->theta_rte + s0 * K, rowsK, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->xi_shp + d0, src->xi_shp + s0, rows1, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->xi_rte + d0, src->xi_rte + s0, rows1, cudaMemcpyDeviceToDevice, dst->stream));
+    if (two_streams) CUDA_TRY(cudaStreamSynchronize(dst->stream));     // src may be written again right away
+    dst->tables_t_valid = false;
+    dst->have_state = true;
     return SCHPF_OK;
 }
 

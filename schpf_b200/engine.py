@@ -133,6 +133,12 @@ class CaviEngine(object):
         _lib.check(self._lib.schpf_step_random_phi(self._h, c_u64(int(seed) & (2 ** 64 - 1)),
                                                    c_int(_flags(freeze_genes, simultaneous, cells_first))))
 
+    def copy_cell_state_from(self, other, dst_row0, src_row0, nrows):
+        """theta / xi of `nrows` cells of `other` starting at `src_row0` -> this engine's cells
+        starting at `dst_row0`, device to device (same device and nfactors)."""
+        _lib.check(self._lib.schpf_copy_cell_state(self._h, c_i64(int(dst_row0)), other._h,
+                                                   c_i64(int(src_row0)), c_i64(int(nrows))))
+
     def copy_gene_state_from(self, other):
         """beta / eta of `other` (same device, ngenes, nfactors) -> this engine, device to device."""
         _lib.check(self._lib.schpf_copy_gene_state(self._h, other._h))

@@ -73,6 +73,14 @@ class OracleEngine(object):
         phi = rng.dirichlet(np.ones(self.nfactors), self.nnz)
         self._iter(freeze_genes, simultaneous, Xphi=self.data[:, None] * phi, cells_first=cells_first)
 
+    def copy_cell_state_from(self, other, dst_row0, src_row0, nrows):
+        if self.st is None:
+            self.set_state()
+        d, s_, n = int(dst_row0), int(src_row0), int(nrows)
+        assert 0 <= d and d + n <= self.ncells and 0 <= s_ and s_ + n <= other.ncells
+        for name in ("theta_shp", "theta_rte", "xi_shp", "xi_rte"):
+            getattr(self.st, name)[d:d + n] = getattr(other.st, name)[s_:s_ + n]
+
     def copy_gene_state_from(self, other):
         o = other.st
         self.set_state(beta=(o.beta_shp, o.beta_rte), eta=(o.eta_shp, o.eta_rte))

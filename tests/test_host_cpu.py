@@ -208,6 +208,9 @@ def test_minibatch_windows_follow_the_reference_schedule():
     np.random.seed(4)
     order = np.arange(10)
     np.random.shuffle(order)
+    from schpf_b200.cavi_loop import MinibatchSchedule
+    sched = MinibatchSchedule(10, 4)
+    assert sched.pieces(0) == [(0, 4)] and sched.pieces(8) == [(8, 2), (0, 2)] and sched.pieces(6) == [(6, 4)]
     np.random.seed(4)
     gen = minibatch_windows(10, 4)
     got = [next(gen) for _ in range(6)]
@@ -221,12 +224,15 @@ def test_minibatch_windows_follow_the_reference_schedule():
     assert_equal(next(gen)[1], order)
 
 
+@pytest.mark.parametrize("device_state", [False, True])
 @pytest.mark.parametrize("cache", [64, 0])
-def test_minibatch_fit_reproduces_seeded_reference(oracle_backend, g_minibatch, monkeypatch, cache):
+def test_minibatch_fit_reproduces_seeded_reference(oracle_backend, g_minibatch, monkeypatch, cache, device_state):
     """Case A of minibatch_small.npz: init, batch shuffle and the batch's t == 0 Dirichlet all
-    come from numpy's stream in the reference's order; with and without per-window engines."""
+    come from numpy's stream in the reference's order; with and without per-window engines,
+    with theta / xi kept on the host or (permuted once) in a master engine."""
     from schpf_b200 import cavi_loop
     monkeypatch.setattr(cavi_loop, "MINIBATCH_ENGINE_CACHE", cache)
+    monkeypatch.setattr(cavi_loop, "MINIBATCH_DEVICE_STATE", device_state)
     g, X = g_minibatch, _X(g_minibatch)
     np.random.seed(int(g["A_seed"]))
     m = scHPF(3, verbose=False).fit(X, batchsize=int(g["A_batchsize"]), min_iter=int(g["A_iters"]),
@@ -238,8 +244,11 @@ def test_minibatch_fit_reproduces_seeded_reference(oracle_backend, g_minibatch, 
     assert_allclose(m.loss, g["A_loss"], rtol=1e-12)
 
 
-def test_minibatch_simultaneous_and_smoothing(oracle_backend, g_minibatch):
+@pytest.mark.parametrize("device_state", [False, True])
+def test_minibatch_simultaneous_and_smoothing(oracle_backend, g_minibatch, monkeypatch, device_state):
     """Case B: reinit=False, beta_theta_simultaneous, loss_smoothing=2."""
+    from schpf_b200 import cavi_loop
+    monkeypatch.setattr(cavi_loop, "MINIBATCH_DEVICE_STATE", device_state)
     g, X = g_minibatch, _X(g_minibatch)
     m = scHPF(3, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]),
               xi=_gam(g, "xi", "B_init_"), theta=_gam(g, "theta", "B_init_"),
@@ -254,7 +263,10 @@ def test_minibatch_simultaneous_and_smoothing(oracle_backend, g_minibatch):
     assert_allclose(m.loss, g["B_loss"], rtol=1e-12)
 
 
-def test_minibatch_edge_cases(oracle_backend, g_minibatch):
+@pytest.mark.parametrize("device_state", [False, True])
+def test_minibatch_edge_cases(oracle_backend, g_minibatch, monkeypatch, device_state):
+    from schpf_b200 import cavi_loop
+    monkeypatch.setattr(cavi_loop, "MINIBATCH_DEVICE_STATE", device_state)
     g, X = g_minibatch, _X(g_minibatch)
     # batchsize 0 / 1 / None / > ncells mean "all cells" (scHPF_.py:627)
     np.random.seed(3)
