@@ -54,7 +54,19 @@ constexpr int SWEEP_MAX_WARPS = 16;
 #define SWEEP_UNROLL2 1
 #endif
 #ifndef SWEEP_STEPS4
-#define SWEEP_STEPS4 1    // K=20: four steps (both stream elements of a trip) as one block, 12 warps x 168 registers
+#define SWEEP_STEPS4 1    // four steps (both stream elements of a trip) as one block, for SWEEP_S4_LO <= KP <= SWEEP_S4_HI
+#endif
+#ifndef SWEEP_S4_LO
+#define SWEEP_S4_LO 20    // measured at KP=20 only (12 warps x 168 registers); the other K are next round's sweep
+#endif
+#ifndef SWEEP_S4_HI
+#define SWEEP_S4_HI 20
+#endif
+#ifndef SWEEP_WSMALL
+#define SWEEP_WSMALL 16   // warps per CTA for KP <= 16
+#endif
+#ifndef SWEEP_WBIG
+#define SWEEP_WBIG 8      // warps per CTA for KP > 32
 #endif
 #ifndef SWEEP_DMMA
 #define SWEEP_DMMA 1      // 1: the lane-pair sum of the partial dot products is an fp64 MMA, not shuffles
@@ -74,7 +86,7 @@ constexpr int SWEEP_MAX_WARPS = 16;
 __host__ __device__ constexpr int sweep_min_ctas(int KP) { return KP == 20 ? SWEEP_MINCTA20 : 1; }
 __host__ __device__ constexpr int sweep_max_warps(int KP)
 {
-    return KP == 20 ? SWEEP_W20 : KP <= 16 ? 16 : KP <= 32 ? SWEEP_WMID : 8;
+    return KP == 20 ? SWEEP_W20 : KP <= 16 ? SWEEP_WSMALL : KP <= 32 ? SWEEP_WMID : SWEEP_WBIG;
 }
 
 template <int KP>
@@ -87,7 +99,7 @@ struct SweepCfg {
     // measured on cfg-3 (K=20): 3.36 ms per sweep pair unrolled against 3.50 rolled; above KP=52
     // the unrolled body spills inside the loop (ptxas -v), so those stay rolled
     static constexpr bool UNROLL2 = SWEEP_UNROLL2 && KP <= 52;
-    static constexpr bool STEPS4 = SWEEP_STEPS4 && KP == 20;
+    static constexpr bool STEPS4 = SWEEP_STEPS4 && KP >= SWEEP_S4_LO && KP <= SWEEP_S4_HI;
 };
 
 template <int N> struct Steps { static constexpr int value = N; };
