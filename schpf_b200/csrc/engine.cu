@@ -749,15 +749,14 @@ int schpf_copy_gene_state(schpf_engine_t *dst, schpf_engine_t *src)
         set_error("schpf_copy_gene_state: source engine has no state");
         return SCHPF_ERR_STATE;
     }
-    // the two handles may use different streams: then finish the source's work first
-    const bool two_streams = dst->stream != src->stream;
-    if (two_streams) CUDA_TRY(cudaStreamSynchronize(src->stream));
+    // the two handles may use different streams: finish the source's work first
+    CUDA_TRY(cudaStreamSynchronize(src->stream));
     const size_t GK = sizeof(double) * (size_t)dst->G * dst->K, Gb = sizeof(double) * (size_t)dst->G;
     CUDA_TRY(cudaMemcpyAsync(dst->beta_shp, src->beta_shp, GK, cudaMemcpyDeviceToDevice, dst->stream));
     CUDA_TRY(cudaMemcpyAsync(dst->beta_rte, src->beta_rte, GK, cudaMemcpyDeviceToDevice, dst->stream));
     CUDA_TRY(cudaMemcpyAsync(dst->eta_shp, src->eta_shp, Gb, cudaMemcpyDeviceToDevice, dst->stream));
     CUDA_TRY(cudaMemcpyAsync(dst->eta_rte, src->eta_rte, Gb, cudaMemcpyDeviceToDevice, dst->stream));
-    if (two_streams) CUDA_TRY(cudaStreamSynchronize(dst->stream));   // src may be stepped again right away
+    CUDA_TRY(cudaStreamSynchronize(dst->stream));   // src may be stepped again right away
     dst->tables_b_valid = false;
     return SCHPF_OK;
 }
