@@ -44,6 +44,35 @@ def greedy_steps(n):
     return steps
 
 
+def greedy_place(lists, classes):
+    """Reference of the placement a one-lane-per-owner layout kernel has to produce for ONE
+    (quarter warp, panel): `lists[o][c]` = panel-local rows of owner o in bank class c (each list
+    is consumed in order).  Returns schedule[step][o] = row or -1 (pad): per step every class is
+    read by at most one owner, every entry appears exactly once, and the number of steps is what
+    `greedy_steps` reports for the count matrix (both apply the same rule)."""
+    O = len(lists)
+    n = np.array([[len(lists[o][c]) for c in range(classes)] for o in range(O)], dtype=np.int64)
+    used = np.zeros_like(n)
+    schedule = []
+    while n.sum() > 0:
+        rs, cs = n.sum(1), n.sum(0)
+        taken = np.zeros(classes, bool)
+        step = [-1] * O
+        for o in np.argsort(-rs, kind="stable"):
+            if rs[o] == 0:
+                continue
+            cand = np.where((n[o] > 0) & ~taken)[0]
+            if cand.size == 0:
+                continue
+            c = cand[np.argmax(cs[cand] * 1000 + n[o, cand])]
+            taken[c] = True
+            step[o] = lists[o][c][used[o, c]]
+            used[o, c] += 1
+            n[o, c] -= 1
+        schedule.append(step)
+    return schedule
+
+
 def simulate(owners_per_warp, per_quarter, classes, n_other, panel_rows, n_per_owner, n_warps, rng, greedy):
     npanel = (n_other + panel_rows - 1) // panel_rows
     real = pad_opt = pad_greedy = 0
