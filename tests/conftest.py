@@ -29,6 +29,11 @@ def g_cavi():
 
 
 @pytest.fixture(scope="session")
+def g_k20():
+    return load_golden("cavi_k20.npz")
+
+
+@pytest.fixture(scope="session")
 def g_project():
     return load_golden("project_cfg1.npz")
 

@@ -18,6 +18,8 @@ Fixtures
   cavi_cfg1.npz     BASELINE cfg-1 (1k x 2k, 100 draws/cell, K = 5): state
                     after 1, 10 and 50 iterations of scHPF._fit from a seeded
                     init (reinit=False, min_iter=max_iter) + loss lists.
+  cavi_k20.npz      50 iterations at K = 20 (800 x 1200) from a seeded init: the BASELINE parity
+                    target (theta / beta within 1e-6 after 50 iterations) at the headline K.
   project_cfg1.npz  scHPF.project of 200 held-out cells onto the 50-iteration
                     model (genes frozen): projected xi/theta + loss.
   reinit_small.npz  fit with reinit=True (the t==0 Dirichlet branch) under a
@@ -199,6 +201,26 @@ def minibatch_small():
     print("minibatch_small: loss A", m.loss, "loss B", base.loss)
 
 
+def cavi_k20():
+    """The BASELINE parity target at the headline K: 50 iterations at K = 20 from a seeded init
+    (800 x 1200, 100 draws per cell)."""
+    X = synth_coo(800, 1200, 100, 20, seed=2)
+    np.random.seed(41)
+    m = scHPF(20, verbose=False)
+    m._initialize(X)
+    out = dict(row=X.row.astype(np.int32), col=X.col.astype(np.int32),
+               data=X.data.astype(np.int32), shape=np.array(X.shape), seed=41,
+               a=m.a, ap=m.ap, bp=m.bp, c=m.c, cp=m.cp, dp=m.dp)
+    out.update(state_dict(m, "init_"))
+    m.fit(X, reinit=False, min_iter=50, max_iter=50, check_freq=10, verbose=False)
+    out.update(state_dict(m, "it50_"))
+    out["it50_loss"] = np.array(m.loss)
+    out["cell_score"] = m.cell_score()
+    out["gene_score"] = m.gene_score()
+    np.savez_compressed(os.path.join(HERE, "cavi_k20.npz"), **out)
+    print("cavi_k20: nnz", X.nnz, "loss", m.loss)
+
+
 def fp32_small():
     """dtype=np.float32 (tests/conftest.py:29 parametrises the reference's tests over it): seeded
     fp32 init, 10 iterations.  The reference's result is mixed precision."""
@@ -221,7 +243,7 @@ def fp32_small():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (kernels_k4, cavi_cfg1, reinit_small, simul_small, minibatch_small, fp32_small):
+    for fn in (kernels_k4, cavi_cfg1, cavi_k20, reinit_small, simul_small, minibatch_small, fp32_small):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):

@@ -101,6 +101,27 @@ def test_estimator_fit_matches_reference(g_cavi):
     assert_allclose(m.mean_negative_pois_llh(X), want, rtol=1e-10)
 
 
+def test_fifty_iterations_at_k20_match_reference(g_k20):
+    """BASELINE.json's parity target -- theta / beta within 1e-6 relative of the reference after 50
+    iterations -- at the headline K = 20, against a golden run of the real reference: asserted at
+    1e-9 (engine level and through the estimator)."""
+    g = _prep_capacity_shapes(g_k20, "init_", 20)
+    with _engine_from(g, "init_", 20) as e:
+        e.step(50)
+        _check_state(e, g_k20, "it50_")
+    X = _X(g_k20)
+    gam = lambda n: HPF_Gamma(g_k20["init_" + n + "_shp"].copy(), g_k20["init_" + n + "_rte"].copy())
+    m = scHPF(20, verbose=False, bp=float(g_k20["bp"]), dp=float(g_k20["dp"]),
+              xi=gam("xi"), theta=gam("theta"), eta=gam("eta"), beta=gam("beta"))
+    m.fit(X, reinit=False, min_iter=50, max_iter=50, check_freq=10)
+    for n in NAMES:
+        assert max_rel(getattr(m, n).vi_shape, g_k20["it50_" + n + "_shp"]) < TOL, n
+        assert max_rel(getattr(m, n).vi_rate, g_k20["it50_" + n + "_rte"]) < TOL, n
+    assert_allclose(m.loss, g_k20["it50_loss"], rtol=1e-11)
+    assert_allclose(m.cell_score(), g_k20["cell_score"], rtol=1e-9)
+    assert_allclose(m.gene_score(), g_k20["gene_score"], rtol=1e-9)
+
+
 def test_estimator_reinit_and_project_match_seeded_reference(g_reinit, g_cavi, g_project):
     g, X = g_reinit, _X(g_reinit)
     np.random.seed(int(g["seed"]))

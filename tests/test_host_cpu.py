@@ -101,6 +101,24 @@ def test_fit_loop_reproduces_reference(oracle_backend, g_cavi, n):
     assert_allclose(m.loss, g["it%d_loss" % n], rtol=1e-12)
 
 
+def test_fifty_iterations_at_k20_reproduce_reference(oracle_backend, g_k20):
+    """BASELINE.json's parity target (theta / beta within 1e-6 of the reference after 50 iterations)
+    at the headline K, for the host loop over the oracle: seeded init drawn here, then 50 iterations."""
+    g, X = g_k20, _X(g_k20)
+    np.random.seed(int(g["seed"]))
+    m = scHPF(20, verbose=False)
+    m._initialize(X)
+    assert m.bp == float(g["bp"]) and m.dp == float(g["dp"])
+    assert_equal(m.theta.vi_shape, g["init_theta_shp"])
+    m.fit(X, reinit=False, min_iter=50, max_iter=50, check_freq=10)
+    for name in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(m, name).vi_shape, g["it50_%s_shp" % name]) < 1e-9
+        assert max_rel(getattr(m, name).vi_rate, g["it50_%s_rte" % name]) < 1e-9
+    assert_allclose(m.loss, g["it50_loss"], rtol=1e-11)
+    assert_allclose(m.cell_score(), g["cell_score"], rtol=1e-9)
+    assert_allclose(m.gene_score(), g["gene_score"], rtol=1e-9)
+
+
 def test_fit_with_reinit_reproduces_seeded_reference(oracle_backend, g_reinit):
     g, X = g_reinit, _X(g_reinit)
     np.random.seed(int(g["seed"]))
