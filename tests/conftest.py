@@ -54,6 +54,11 @@ def g_minibatch():
 
 
 @pytest.fixture(scope="session")
+def g_trials():
+    return load_golden("trials_small.npz")
+
+
+@pytest.fixture(scope="session")
 def g_fp32():
     return load_golden("fp32_small.npz")
 

@@ -28,6 +28,8 @@ Fixtures
   minibatch_small.npz  scHPF.fit(batchsize=...) (schpf/scHPF_.py:626-631, 642-650, 686-704):
                     A: reinit=True, 240 cells in windows of 64 (wrapping), 9 iterations;
                     B: reinit=False, windows of 100, beta_theta_simultaneous, loss_smoothing=2.
+  trials_small.npz  run_trials: three seeded restarts (final losses in return order, the best model)
+                    and two restarts scored on projected validation cells.
   fp32_small.npz    the same loop with dtype=np.float32 (mixed precision in the reference).
 """
 import os
@@ -221,6 +223,33 @@ def cavi_k20():
     print("cavi_k20: nnz", X.nnz, "loss", m.loss)
 
 
+def trials_small():
+    """run_trials (scHPF_.py:968-1148): three seeded restarts, and two restarts scored on
+    projected validation cells (loss.py:37-102)."""
+    import contextlib
+    import io
+    from schpf import run_trials
+    X = synth_coo(200, 300, 40, 3, seed=5)
+    V = synth_coo(40, 300, 40, 3, seed=6)
+    out = dict(row=X.row.astype(np.int32), col=X.col.astype(np.int32), data=X.data.astype(np.int32),
+               shape=np.array(X.shape), vrow=V.row.astype(np.int32), vcol=V.col.astype(np.int32),
+               vdata=V.data.astype(np.int32), vshape=np.array(V.shape))
+    np.random.seed(51)
+    with contextlib.redirect_stdout(io.StringIO()):
+        best, others = run_trials(X, 3, ntrials=3, min_iter=4, max_iter=4, check_freq=2, verbose=False,
+                                  return_all=True)
+    out.update(A_seed=51, A_final_losses=np.array([best.loss[-1]] + [m.loss[-1] for m in others]),
+               A_best_loss=np.array(best.loss), A_best_bp=best.bp, A_best_dp=best.dp)
+    out.update(state_dict(best, "A_best_"))
+    np.random.seed(52)
+    with contextlib.redirect_stdout(io.StringIO()):
+        vbest = run_trials(X, 3, ntrials=2, min_iter=4, max_iter=4, check_freq=2, verbose=False, vcells=V)
+    out.update(B_seed=52, B_best_loss=np.array(vbest.loss))
+    out.update(state_dict(vbest, "B_best_"))
+    np.savez_compressed(os.path.join(HERE, "trials_small.npz"), **out)
+    print("trials_small: A", out["A_final_losses"], "B", vbest.loss)
+
+
 def fp32_small():
     """dtype=np.float32 (tests/conftest.py:29 parametrises the reference's tests over it): seeded
     fp32 init, 10 iterations.  The reference's result is mixed precision."""
@@ -243,7 +272,7 @@ def fp32_small():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (kernels_k4, cavi_cfg1, cavi_k20, reinit_small, simul_small, minibatch_small, fp32_small):
+    for fn in (kernels_k4, cavi_cfg1, cavi_k20, reinit_small, simul_small, minibatch_small, trials_small, fp32_small):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):

@@ -448,6 +448,30 @@ def test_run_trials_on_device(g_reinit, g_project, capsys):
     assert [p.nfactors for p in pool] == [2, 3] and all(np.isfinite(p.loss[-1]) for p in pool)
 
 
+def test_run_trials_reproduces_the_reference(g_trials, capsys):
+    """run_trials under a fixed numpy seed against the reference's own run_trials: the final losses
+    of all restarts in return order, the selected model, and the variant scored on projected
+    validation cells (scHPF_.py:968-1148, loss.py:37-102)."""
+    from schpf_b200 import run_trials
+    g = g_trials
+    X = coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(int(v) for v in g["shape"]))
+    V = coo_matrix((g["vdata"], (g["vrow"], g["vcol"])), shape=tuple(int(v) for v in g["vshape"]))
+    np.random.seed(int(g["A_seed"]))
+    best, others = run_trials(X, 3, ntrials=3, min_iter=4, max_iter=4, check_freq=2, verbose=False, return_all=True)
+    assert_allclose([best.loss[-1]] + [m.loss[-1] for m in others], g["A_final_losses"], rtol=1e-10)
+    assert_allclose(best.loss, g["A_best_loss"], rtol=1e-10)
+    assert best.bp == float(g["A_best_bp"]) and best.dp == float(g["A_best_dp"])
+    for n in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(best, n).vi_shape, g["A_best_%s_shp" % n]) < 1e-9
+        assert max_rel(getattr(best, n).vi_rate, g["A_best_%s_rte" % n]) < 1e-9
+    np.random.seed(int(g["B_seed"]))
+    vbest = run_trials(X, 3, ntrials=2, min_iter=4, max_iter=4, check_freq=2, verbose=False, vcells=V)
+    assert_allclose(vbest.loss, g["B_best_loss"], rtol=1e-10)
+    for n in ("theta", "beta"):
+        assert max_rel(getattr(vbest, n).vi_shape, g["B_best_%s_shp" % n]) < 1e-9
+    assert "train:" in capsys.readouterr().out
+
+
 def test_packed_and_wide_entry_streams_agree():
     """The opt-in 4-byte stream format (row | count<<12 | pad<<31) needs all counts below 2^19;
     otherwise the 8-byte format is kept.  Same numbers either way."""

@@ -386,6 +386,30 @@ def test_run_trials_picks_lowest_loss_like_the_reference(oracle_backend, g_reini
     assert isinstance(m.loss[-1], list) and len(m.loss) == 4          # 3 checks + the reprojection's list
 
 
+def test_run_trials_reproduces_the_reference(oracle_backend, g_trials, capsys):
+    """run_trials under a fixed numpy seed against the reference's own run_trials: the final losses
+    of all restarts in return order, the selected model, and the variant scored on projected
+    validation cells (scHPF_.py:968-1148, loss.py:37-102)."""
+    from schpf_b200 import run_trials
+    g = g_trials
+    X = coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(int(v) for v in g["shape"]))
+    V = coo_matrix((g["vdata"], (g["vrow"], g["vcol"])), shape=tuple(int(v) for v in g["vshape"]))
+    np.random.seed(int(g["A_seed"]))
+    best, others = run_trials(X, 3, ntrials=3, min_iter=4, max_iter=4, check_freq=2, verbose=False, return_all=True)
+    assert_allclose([best.loss[-1]] + [m.loss[-1] for m in others], g["A_final_losses"], rtol=1e-11)
+    assert_allclose(best.loss, g["A_best_loss"], rtol=1e-11)
+    assert best.bp == float(g["A_best_bp"]) and best.dp == float(g["A_best_dp"])
+    for n in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(best, n).vi_shape, g["A_best_%s_shp" % n]) < 1e-10
+        assert max_rel(getattr(best, n).vi_rate, g["A_best_%s_rte" % n]) < 1e-10
+    np.random.seed(int(g["B_seed"]))
+    vbest = run_trials(X, 3, ntrials=2, min_iter=4, max_iter=4, check_freq=2, verbose=False, vcells=V)
+    assert_allclose(vbest.loss, g["B_best_loss"], rtol=1e-11)
+    for n in ("theta", "beta"):
+        assert max_rel(getattr(vbest, n).vi_shape, g["B_best_%s_shp" % n]) < 1e-10
+    assert "train:" in capsys.readouterr().out
+
+
 def test_run_trials_pool_over_devices(oracle_backend, g_reinit):
     from schpf_b200 import run_trials_pool
     X = _X(g_reinit)
