@@ -257,11 +257,16 @@ class scHPF(BaseEstimator):
                                      beta=self.beta if beta is None else beta)
 
     def cellmean_negative_pois_llh(self, X, theta=None, beta=None):
+        """Mean negative llh of the stored entries, averaged per cell (scHPF_.py:395-411): per cell
+        the sum over its triples divided by the number of DISTINCT genes among them (the reference
+        takes the count from a csr copy, which merges duplicate triples).  nan for empty cells."""
         theta = self.theta if theta is None else theta
         assert theta.vi_shape.shape[0] == X.shape[0]
         llh = self.pois_llh_pointwise(X=X, theta=theta, beta=beta)
-        sums = np.bincount(X.row, weights=-llh, minlength=X.shape[0])
-        counts = np.bincount(X.row, minlength=X.shape[0])
+        ncells, ngenes = X.shape
+        sums = np.bincount(X.row, weights=-llh, minlength=ncells)
+        distinct = np.unique(np.asarray(X.row, dtype=np.int64) * ngenes + X.col)
+        counts = np.bincount(distinct // ngenes, minlength=ncells)
         with np.errstate(invalid='ignore', divide='ignore'):
             return sums / counts
 

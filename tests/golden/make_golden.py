@@ -241,6 +241,12 @@ def trials_small():
     out.update(A_seed=51, A_final_losses=np.array([best.loss[-1]] + [m.loss[-1] for m in others]),
                A_best_loss=np.array(best.loss), A_best_bp=best.bp, A_best_dp=best.dp)
     out.update(state_dict(best, "A_best_"))
+    out["A_cellmean"] = best.cellmean_negative_pois_llh(X)                   # scHPF_.py:395-411
+    # the same with duplicate triples: the reference counts DISTINCT genes per cell (its csr sums them)
+    dup = np.concatenate([np.arange(X.nnz), np.arange(0, X.nnz, 7)])
+    Xd = coo_matrix((X.data[dup], (X.row[dup], X.col[dup])), shape=X.shape)
+    out["dup_index"] = dup
+    out["A_cellmean_dup"] = best.cellmean_negative_pois_llh(Xd)
     np.random.seed(52)
     with contextlib.redirect_stdout(io.StringIO()):
         vbest = run_trials(X, 3, ntrials=2, min_iter=4, max_iter=4, check_freq=2, verbose=False, vcells=V)

@@ -402,6 +402,11 @@ def test_run_trials_reproduces_the_reference(oracle_backend, g_trials, capsys):
     for n in ("theta", "beta", "xi", "eta"):
         assert max_rel(getattr(best, n).vi_shape, g["A_best_%s_shp" % n]) < 1e-10
         assert max_rel(getattr(best, n).vi_rate, g["A_best_%s_rte" % n]) < 1e-10
+    # per-cell mean of the pointwise llh (scHPF_.py:395-411), also with duplicate triples
+    assert_allclose(best.cellmean_negative_pois_llh(X), g["A_cellmean"], rtol=1e-11)
+    dup = g["dup_index"]
+    Xd = coo_matrix((X.data[dup], (X.row[dup], X.col[dup])), shape=X.shape)
+    assert_allclose(best.cellmean_negative_pois_llh(Xd), g["A_cellmean_dup"], rtol=1e-11)
     np.random.seed(int(g["B_seed"]))
     vbest = run_trials(X, 3, ntrials=2, min_iter=4, max_iter=4, check_freq=2, verbose=False, vcells=V)
     assert_allclose(vbest.loss, g["B_best_loss"], rtol=1e-11)
