@@ -118,7 +118,8 @@ int schpf_destroy(schpf_engine_t *h);
  * "packed_entries" (1 = 4-byte stream entries when every count is < 2^19: half the
  * resident layout, slightly slower sweeps), "overlap_exchange" (default 1: with an attached
  * communicator schpf_step runs the all-reduce on a second stream underneath the cells-own sweep;
- * 0 = in order on the engine's stream) */
+ * 0 = in order on the engine's stream), "lanes" (default 1: K in 13..20 and 29..32 run the
+ * one-lane-per-owner sweep; 0 = lane-pair sweep for every K), "rank_per_range" (-1 automatic) */
 int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value);
 
 /* The sparse count matrix as COO triples (X.row, X.col, X.data of a
@@ -203,12 +204,21 @@ int schpf_llh_pointwise(schpf_engine_t *h, double *out_host_nnz);
 /* Xphi of the resident state (nnz x K, host) -- small inputs, debugging */
 int schpf_xphi_debug(schpf_engine_t *h, double *out_host_nnz_x_K);
 
+/* The device layout of one sweep direction (side 0: cells own, 1: genes own) decoded back to COO
+ * triples, in stream order: `own` / `oth` are the owner's and the other axis' GLOBAL indices, pad
+ * entries have own = oth = -1 and count 0.  *n_out = entries in the stream (pads included); call
+ * with null buffers to query it.  Test hook for the exact integer round trip
+ * multiset{(row, col, y)} in == out; small matrices. */
+int schpf_layout_dump(schpf_engine_t *h, int side, int64_t capacity, int32_t *own, int32_t *oth,
+                      int32_t *count, int64_t *n_out);
+
 /* wait for all enqueued work of this handle */
 int schpf_synchronize(schpf_engine_t *h);
 
 /* counters: what = "nnz", "padded_nnz_cells", "padded_nnz_genes",
- * "sweep_launches", "kernel_launches", "sweep_ms" (needs option timing=1;
- * synchronises), "iterations", "slow_path_hits", "layout_bytes" */
+ * "sweep_launches", "shape_sweep_launches", "kernel_launches", "sweep_ms" / "sweep_ms_shape" /
+ * "sweep_ms_llh" (need option timing=1; synchronise), "iterations", "slow_path_hits",
+ * "layout_bytes", "panel_rows", "warps_per_cta", "lanes" (1 = one-lane-per-owner sweep) */
 int schpf_counter(schpf_engine_t *h, const char *what, double *value);
 
 #ifdef __cplusplus

@@ -59,6 +59,7 @@ SIGNATURES = {
     "schpf_loss_parts": [c_vp, p_dbl, ctypes.POINTER(c_i64)],
     "schpf_llh_pointwise": [c_vp, p_dbl],
     "schpf_xphi_debug": [c_vp, p_dbl],
+    "schpf_layout_dump": [c_vp, c_int, c_i64, p_i32, p_i32, p_i32, ctypes.POINTER(c_i64)],
     "schpf_synchronize": [c_vp],
     "schpf_counter": [c_vp, ctypes.c_char_p, p_dbl],
 }

@@ -47,7 +47,7 @@ void trace_mark(cudaStream_t stream, const char *what);
 __host__ __device__ constexpr int kp_of(int K) { return (K + 3) & ~3; }
 __host__ __device__ constexpr int stride_of_kp(int KP) { return ((KP / 4) & 1) ? KP : KP + 4; }
 
-constexpr int GROUPS_PER_WARP = 16;          // lane pairs
+constexpr int GROUPS_PER_WARP = 16;          // lane pairs (sweep.cu); the one-lane kernel has 32 owners per warp
 constexpr double TINY_NORMALIZER = 1e-280;   // below this the factored softmax is redone in log space
 
 // ------------------------------------------------------- device helpers ----
@@ -125,6 +125,30 @@ __device__ __forceinline__ double pair_sum_mma(double p, double sel)
                  : "d"(p), "d"(sel), "d"(0.0), "d"(0.0));
     return d0;
 }
+
+// Tables the sweeps read (Et/Eb, Xt/Xb) come in two geometries, chosen per K:
+//   pairs (sweep.cu):       one plane, rows of ST doubles        -> KA = ST, KB = 0
+//   lanes (sweep_lanes.cu): plane A = first KA = 16*NA doubles of every row (row stride KA), then
+//                           plane B = the last KB = 4 doubles (row stride KB) starting at offB = n_pad*KA
+struct TabGeom {
+    int KA, KB;
+    int64_t offB;
+};
+__host__ __device__ __forceinline__ int64_t tab_index(const TabGeom &g, int64_t i, int k)
+{
+    return k < g.KA ? i * g.KA + k : g.offB + i * g.KB + (k - g.KA);
+}
+// padded row length of the one-lane kernel's classes: K 13..16 -> 16, 17..20 -> 20, 29..32 -> 32 (else unsupported)
+__host__ __device__ constexpr int lanes_kp_of(int K)
+{
+    return (K >= 13 && K <= 16) ? 16 : (K >= 17 && K <= 20) ? 20 : (K >= 29 && K <= 32) ? 32 : 0;
+}
+
+// y as the HIGH WORD of its double: counts below 2^21 have an all-zero low word, so the sweep
+// builds the double from the stream word with no conversion instruction (I2F.F64 runs on the
+// fp64 pipe the kernel is short of)
+constexpr int YHI_MAX_COUNT_BITS = 21;
+constexpr int TINY_NORMALIZER_HI = 0x05cd0b15;   // high word of TINY_NORMALIZER (1e-280)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -226,16 +250,27 @@ struct SideLayout {
     int64_t padded_entries = 0;
     int32_t *own_id = nullptr;   // [nblocks * W * 16] slot -> owner id, -1 = empty slot
     int64_t *seg_ptr = nullptr;  // [(nblocks * W) * (npanel + 1)] in step pairs
-    void *entries = nullptr;     // [total_pairs * 16] x (int4 wide | int2 packed): two steps per element
+    void *entries = nullptr;     // [total_pairs * opw] x (int4 wide | int2 packed): two steps per element
     bool packed = false;
+    int opw = GROUPS_PER_WARP;   // owners per warp: 16 (one per lane pair) or 32 (one per lane)
+    bool free_mode = false;      // no bank-class schedule (tables whose rows all start at bank group 0)
+    bool ranked_per_range = false;   // owners re-ranked by their count inside every panel range
+    bool yhi = false;            // count field holds the high word of (double)count
+    int64_t n_slots = 0;         // nblocks * warps * opw
     size_t bytes = 0;
     cudaStream_t stream = nullptr;   // stream the buffers were allocated on (pool_free)
     void release();
 };
 
+enum LayoutFlags { LAYOUT_FREE = 1, LAYOUT_RANK_PER_RANGE = 2, LAYOUT_YHI = 4, LAYOUT_SINGLE_PANEL_RANGES = 8,
+                   LAYOUT_ROTATE_CLASS = 16 };
 int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int32_t *d_own,
                       const int32_t *d_oth, const int32_t *d_val, int64_t n_own, int64_t n_oth,
-                      int panel_rows, int warps, int target_ctas, bool packed);
+                      int panel_rows, int warps, int target_ctas, bool packed, int owners_per_warp = GROUPS_PER_WARP,
+                      int flags = 0);
+// debug / tests: the layout's entries decoded back to (owner, other, count) triples, host arrays of
+// L.padded_entries elements each (pads: count 0 and other = -1); returns the number written
+int64_t dump_side_layout(const SideLayout &L, cudaStream_t stream, int32_t *own, int32_t *oth, int32_t *cnt);
 
 // frees the per-device scratch block the layout builds keep between calls
 int release_layout_scratch(int device);
@@ -255,21 +290,43 @@ struct SweepArgs {
     const double *oth_elog;  // [n_oth x K]
     double *direct;          // [n_own x K]  fallback contributions, already y*phi
     unsigned long long *slow_hits;
+    // nonzeros whose factored normaliser underflowed are queued here and redone in log space by
+    // slow_fixup_kernel after the sweep (the exp() code stays out of the hot loop's register budget)
+    int4 *slow_queue;                 // {owner, other (global), y as double hi, lo}
+    unsigned long long *slow_count;
+    unsigned int slow_cap;
     int K;
     int npanel, panel_rows, warps, panels_per_range, nranges;
+    int64_t own_range_stride;   // 0, or n_slots when owners are ranked per range (own_id is [nranges][n_slots])
+    int64_t own_offB, oth_offB; // lanes geometry: start of plane B in the two tables
 };
 
+// append one underflowed nonzero to the sweep's queue (dropped beyond slow_cap: the fix-up kernel
+// then raises the engine's sticky overflow flag)
+__device__ __forceinline__ void slow_enqueue(const SweepArgs &A, int own, int oth_global, double y)
+{
+    const unsigned long long at = atomicAdd(A.slow_count, 1ULL);
+    if (at < A.slow_cap) A.slow_queue[at] = make_int4(own, oth_global, __double2hiint(y), __double2loint(y));
+}
+int launch_slow_fixup(cudaStream_t s, const SweepArgs &args, int *overflow_flag);
+
 int launch_sweep(int mode, int K, const SideLayout &L, const SweepArgs &args, cudaStream_t stream);
+// one-lane-per-owner kernels (sweep_lanes.cu)
+bool lanes_supported(int K);
+int lanes_default_warps(int K);
+int launch_lane_sweep(int mode, int K, const SideLayout &L, const SweepArgs &args, cudaStream_t stream);
+inline size_t lane_sweep_smem_bytes(int KP, int panel_rows) { return (size_t)panel_rows * KP * 8 + 16 + 16 * 8; }
+int lanes_max_panel_rows(int K);
 size_t sweep_smem_bytes(int K, int panel_rows);
 int max_panel_rows(int K, int ctas_per_sm);
 
 // ------------------------------------------------ dense / per-nnz kernels ---
-int launch_prep_side(cudaStream_t s, int64_t n, int K, const double *shp, const double *rte,
+int launch_prep_side(cudaStream_t s, int64_t n, int K, const TabGeom &tg, const double *shp, const double *rte,
                      double *elog, double *E, double *colsum /* K, accumulated; may be null */);
-int launch_ex_table(cudaStream_t s, int64_t n, int K, const double *shp, const double *rte, double *X);
-int launch_fold(cudaStream_t s, int64_t n, int K, const double *E, const double *acc,
+int launch_ex_table(cudaStream_t s, int64_t n, int K, const TabGeom &tg, const double *shp, const double *rte, double *X);
+int launch_fold(cudaStream_t s, int64_t n, int K, const TabGeom &tg, const double *E, const double *acc,
                 const double *direct, double *out);
-int launch_finalize(cudaStream_t s, int64_t n, int K, double prior_shape, double prior_rate,
+int launch_finalize(cudaStream_t s, int64_t n, int K, const TabGeom &tg, double prior_shape, double prior_rate,
                     const double *folded /* n x K, or null */, const double *E, const double *acc,
                     const double *direct, const double *other_colsum, const double *cap_shp,
                     double *cap_rte, double *shp, double *rte, double *elog, double *Etab,

@@ -54,7 +54,7 @@ __device__ __forceinline__ void block_colsum_atomic(int K, F val, double *colsum
 // over the rows its warp visits (summed over the CTA's warps, then one atomicAdd per column and CTA).
 template <bool UPDATE>
 __global__ void __launch_bounds__(DENSE_THREADS)
-finalize_kernel(int64_t n, int K, int ST, double prior_shape, double prior_rate,
+finalize_kernel(int64_t n, int K, TabGeom tg, double prior_shape, double prior_rate,
                 const double *__restrict__ folded, const double *__restrict__ acc,
                 const double *__restrict__ direct, const double *__restrict__ other_colsum,
                 const double *__restrict__ cap_shp, double *__restrict__ cap_rte,
@@ -83,7 +83,7 @@ finalize_kernel(int64_t n, int K, int ST, double prior_shape, double prior_rate,
                 if (UPDATE) {
                     double v;
                     if (folded) v = folded[i * K + k];
-                    else v = fma(Etab[i * (int64_t)ST + k], acc[i * K + k], direct[i * K + k]);
+                    else v = fma(Etab[tab_index(tg, i, k)], acc[i * K + k], direct[i * K + k]);
                     sk[t] = prior_shape + v;
                     rk[t] = cap_ex + oc[t];
                     shp[i * K + k] = sk[t];
@@ -109,7 +109,7 @@ finalize_kernel(int64_t n, int K, int ST, double prior_shape, double prior_rate,
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const int k = lane + 32 * t;
-            if (k < K) Etab[i * (int64_t)ST + k] = exp(el[t] - m);
+            if (k < K) Etab[tab_index(tg, i, k)] = exp(el[t] - m);
         }
     }
     if (colsum_out) {
@@ -130,19 +130,19 @@ finalize_kernel(int64_t n, int K, int ST, double prior_shape, double prior_rate,
 }
 
 // e_x table in the padded sweep layout (hpf_numba.py:33-41)
-__global__ void ex_table_kernel(int64_t n, int K, int ST, const double *__restrict__ shp,
+__global__ void ex_table_kernel(int64_t n, int K, TabGeom tg, const double *__restrict__ shp,
                                 const double *__restrict__ rte, double *__restrict__ X)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * K) return;
     const int64_t i = idx / K;
     const int k = (int)(idx - i * K);
-    X[i * ST + k] = shp[idx] / rte[idx];
+    X[tab_index(tg, i, k)] = shp[idx] / rte[idx];
 }
 
 // out[i,k] = E[i,k] * acc[i,k] + direct[i,k] : this shard's part of
 // sum_{nonzeros of gene i} Xphi[:,k]  (the loop at hpf_numba.py:152-155)
-__global__ void fold_kernel(int64_t n, int K, int ST, const double *__restrict__ E,
+__global__ void fold_kernel(int64_t n, int K, TabGeom tg, const double *__restrict__ E,
                             const double *__restrict__ acc, const double *__restrict__ direct,
                             double *__restrict__ out)
 {
@@ -150,7 +150,7 @@ __global__ void fold_kernel(int64_t n, int K, int ST, const double *__restrict__
     if (idx >= n * K) return;
     const int64_t i = idx / K;
     const int k = (int)(idx - i * K);
-    out[idx] = fma(E[i * ST + k], acc[idx], direct[idx]);
+    out[idx] = fma(E[tab_index(tg, i, k)], acc[idx], direct[idx]);
 }
 
 // The reference's E-step written literally (hpf_numba.py:98-112): one thread
@@ -178,6 +178,35 @@ __global__ void literal_kernel(int64_t nnz, int K, const int32_t *__restrict__ r
         if (xphi_out) xphi_out[i * K + k] = v;
         if (direct_t) atomicAdd(direct_t + r * K + k, v);
         if (direct_b) atomicAdd(direct_b + c * K + k, v);
+    }
+}
+
+// The queued nonzeros of one sweep whose factored normaliser underflowed, redone exactly as the
+// reference does every nonzero (hpf_numba.py:98-112: log space, max subtracted) and added to the
+// owner's `direct` row.  Launched after every shape sweep with a small fixed grid; the queue is
+// empty unless priors are far below 1e-2, and the kernel then costs one read.
+__global__ void slow_fixup_kernel(const int4 *__restrict__ queue, const unsigned long long *__restrict__ count,
+                                  unsigned int cap, int K, const double *__restrict__ own_elog,
+                                  const double *__restrict__ oth_elog, double *__restrict__ direct,
+                                  unsigned long long *__restrict__ slow_hits, int *__restrict__ overflow)
+{
+    unsigned long long n = *count;
+    if (n == 0) return;
+    if (n > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 1);
+        n = cap;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(slow_hits, n);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const int4 q = queue[i];
+        const double y = __hiloint2double(q.z, q.w);
+        const double *eo = own_elog + (int64_t)q.x * K, *et = oth_elog + (int64_t)q.y * K;
+        double largest = -INFINITY, normalizer = 0.0;
+        for (int k = 0; k < K; ++k) largest = fmax(largest, eo[k] + et[k]);
+        for (int k = 0; k < K; ++k) normalizer += exp(eo[k] + et[k] - largest);
+        for (int k = 0; k < K; ++k)
+            atomicAdd(direct + (int64_t)q.x * K + k, y * exp(eo[k] + et[k] - largest) / normalizer);
     }
 }
 
@@ -321,6 +350,7 @@ __global__ void validate_coo_kernel(int64_t nnz, const int32_t *__restrict__ row
     if (col[i] < 0 || col[i] >= G) f |= 2;
     if (data[i] < 0) f |= 4;
     if (data[i] >= (1 << PACKED_COUNT_BITS)) f |= 8;      // too large for the packed stream format
+    if (data[i] >= (1 << YHI_MAX_COUNT_BITS)) f |= 16;    // low word of (double)count is not zero
     if (f) atomicOr(flag, f);
 }
 
@@ -382,46 +412,52 @@ __global__ void capacity_rate_kernel(int64_t n, int K, const double *__restrict_
         }                                                                                   \
     } while (0)
 
-int launch_prep_side(cudaStream_t s, int64_t n, int K, const double *shp, const double *rte,
+int launch_slow_fixup(cudaStream_t s, const SweepArgs &A, int *overflow_flag)
+{
+    slow_fixup_kernel<<<64, 128, 0, s>>>(A.slow_queue, A.slow_count, A.slow_cap, A.K, A.own_elog, A.oth_elog,
+                                         A.direct, A.slow_hits, overflow_flag);
+    LAUNCH_CHECK();
+    return SCHPF_OK;
+}
+
+int launch_prep_side(cudaStream_t s, int64_t n, int K, const TabGeom &tg, const double *shp, const double *rte,
                      double *elog, double *E, double *colsum)
 {
     if (n <= 0) return SCHPF_OK;
-    const int ST = stride_of_kp(kp_of(K));
     finalize_kernel<false><<<finalize_grid(n), DENSE_THREADS, 0, s>>>(
-        n, K, ST, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+        n, K, tg, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
         const_cast<double *>(shp), const_cast<double *>(rte), elog, E, colsum);
     LAUNCH_CHECK();
     return SCHPF_OK;
 }
 
-int launch_finalize(cudaStream_t s, int64_t n, int K, double prior_shape, double prior_rate,
+int launch_finalize(cudaStream_t s, int64_t n, int K, const TabGeom &tg, double prior_shape, double prior_rate,
                     const double *folded, const double *E, const double *acc, const double *direct,
                     const double *other_colsum, const double *cap_shp, double *cap_rte, double *shp,
                     double *rte, double *elog, double *Etab, double *colsum_out)
 {
     if (n <= 0) return SCHPF_OK;
     (void)E;  // the factored table read for the fold is the one being rewritten (Etab)
-    const int ST = stride_of_kp(kp_of(K));
     finalize_kernel<true><<<finalize_grid(n), DENSE_THREADS, 0, s>>>(
-        n, K, ST, prior_shape, prior_rate, folded, acc, direct, other_colsum, cap_shp, cap_rte, shp,
+        n, K, tg, prior_shape, prior_rate, folded, acc, direct, other_colsum, cap_shp, cap_rte, shp,
         rte, elog, Etab, colsum_out);
     LAUNCH_CHECK();
     return SCHPF_OK;
 }
 
-int launch_ex_table(cudaStream_t s, int64_t n, int K, const double *shp, const double *rte, double *X)
+int launch_ex_table(cudaStream_t s, int64_t n, int K, const TabGeom &tg, const double *shp, const double *rte, double *X)
 {
     if (n <= 0) return SCHPF_OK;
-    ex_table_kernel<<<blocks_for(n * K, 256), 256, 0, s>>>(n, K, stride_of_kp(kp_of(K)), shp, rte, X);
+    ex_table_kernel<<<blocks_for(n * K, 256), 256, 0, s>>>(n, K, tg, shp, rte, X);
     LAUNCH_CHECK();
     return SCHPF_OK;
 }
 
-int launch_fold(cudaStream_t s, int64_t n, int K, const double *E, const double *acc,
+int launch_fold(cudaStream_t s, int64_t n, int K, const TabGeom &tg, const double *E, const double *acc,
                 const double *direct, double *out)
 {
     if (n <= 0) return SCHPF_OK;
-    fold_kernel<<<blocks_for(n * K, 256), 256, 0, s>>>(n, K, stride_of_kp(kp_of(K)), E, acc, direct, out);
+    fold_kernel<<<blocks_for(n * K, 256), 256, 0, s>>>(n, K, tg, E, acc, direct, out);
     LAUNCH_CHECK();
     return SCHPF_OK;
 }

@@ -124,6 +124,11 @@ struct schpf_engine {
     int64_t C = 0, G = 0, nnz = 0;
     int K = 0, ST = 0;
     int64_t C_pad = 0, G_pad = 0;
+    // sweep family and table geometry (common.cuh TabGeom): lanes = one-lane-per-owner kernels
+    bool lanes = false;
+    int KA = 0, KB = 0;
+    TabGeom geom_t() const { return TabGeom{KA, KB, C_pad * KA}; }
+    TabGeom geom_b() const { return TabGeom{KA, KB, G_pad * KA}; }
 
     // options
     int opt_panel_rows = 0;     // 0 = largest that fits
@@ -132,6 +137,9 @@ struct schpf_engine {
     int opt_variant = 0;
     int opt_timing = 0;
     int opt_packed_entries = 0; // 1 = 4-byte stream entries when every count is < 2^19
+    int opt_lanes = 1;          // 0 = lane-pair kernels for every K (sweep.cu)
+    int opt_rank_per_range = -1; // -1 = automatic (on for streams without a bank schedule); 0 / 1
+    int opt_free_schedule = -1;  // K 17..20 (plane B): 1 = no bank schedule (rotated class order instead), 0 = 4x4 colouring
     int64_t row_offset = 0;     // global index of local cell 0 (random-phi stream)
 
     bool have_coo = false, have_hyper = false, have_state = false;
@@ -154,9 +162,15 @@ struct schpf_engine {
     int partials_cap = 0;
     double *scalars = nullptr;                       // [0] llh sum, [1] lgamma sum
     unsigned long long *slow_hits = nullptr;
+    // queues of underflowed nonzeros, one per sweep direction (common.cuh slow_enqueue); the two
+    // counters are the first 16 doubles of `accum`, so the per-iteration memset clears them too
+    int4 *slow_q_t = nullptr, *slow_q_b = nullptr;
+    unsigned int slow_cap = 0;
+    int *overflow = nullptr;     // sticky: a queue overflowed (reported at the next read-out)
     int *flag = nullptr;
     double lgamma_sum = 0.0;
 
+    int64_t tab_t_elems = 0, tab_b_elems = 0;        // allocated sizes of Et/Xt and Eb/Xb
     int32_t *row = nullptr, *col = nullptr, *data = nullptr;
     SideLayout cells, genes;
 
@@ -168,13 +182,19 @@ struct schpf_engine {
     cudaEvent_t ev_folded = nullptr, ev_reduced = nullptr;
 
     // counters
-    double n_iterations = 0, n_sweeps = 0, n_launches = 0;
+    double n_iterations = 0, n_sweeps = 0, n_shape_sweeps = 0, n_launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<int> ev_mode;            // sweep mode of every recorded event pair
     size_t ev_used = 0;
-    double sweep_ms_accum = 0.0;
+    double sweep_ms_accum = 0.0, sweep_ms_shape = 0.0, sweep_ms_llh = 0.0;
 };
 
 namespace {
+
+#ifndef LANES_FREE20_DEFAULT
+#define LANES_FREE20_DEFAULT 0
+#endif
+constexpr int64_t ACCUM_HEADER = 16;   // doubles in front of the accumulators: the two queue counters
 
 template <typename T>
 int dev_alloc(T **p, int64_t n)
@@ -203,6 +223,8 @@ int check_handle(schpf_engine *h)
 
 void free_coo(schpf_engine *h)
 {
+    dev_free(h->slow_q_t);
+    dev_free(h->slow_q_b);
     dev_free(h->row);
     dev_free(h->col);
     dev_free(h->data);
@@ -220,15 +242,19 @@ int timed_sweep(schpf_engine *h, int mode, const SideLayout &L, const SweepArgs 
             CUDA_TRY(cudaEventCreate(&a));
             CUDA_TRY(cudaEventCreate(&b));
             h->ev_pool.emplace_back(a, b);
+            h->ev_mode.push_back(0);
         }
+        h->ev_mode[h->ev_used] = mode;
         e0 = h->ev_pool[h->ev_used].first;
         e1 = h->ev_pool[h->ev_used].second;
         ++h->ev_used;
         CUDA_TRY(cudaEventRecord(e0, h->stream));
     }
-    RC_TRY(launch_sweep(mode, h->K, L, args, h->stream));
+    if (L.opw == 32) RC_TRY(launch_lane_sweep(mode, h->K, L, args, h->stream));
+    else RC_TRY(launch_sweep(mode, h->K, L, args, h->stream));
     if (h->opt_timing) CUDA_TRY(cudaEventRecord(e1, h->stream));
     h->n_sweeps += 1;
+    if (mode == SWEEP_SHAPE) h->n_shape_sweeps += 1;
     h->n_launches += 1;
     return SCHPF_OK;
 }
@@ -241,6 +267,7 @@ int collect_timing(schpf_engine *h)
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_pool[i].first, h->ev_pool[i].second));
         h->sweep_ms_accum += ms;
+        (h->ev_mode[i] == SWEEP_SHAPE ? h->sweep_ms_shape : h->sweep_ms_llh) += ms;
     }
     h->ev_used = 0;
     return SCHPF_OK;
@@ -254,12 +281,20 @@ SweepArgs side_args(schpf_engine *h, const SideLayout &L)
     A.seg_ptr = L.seg_ptr;
     A.entries = L.entries;
     A.slow_hits = h->slow_hits;
+    A.slow_queue = &L == &h->cells ? h->slow_q_t : h->slow_q_b;
+    A.slow_count = reinterpret_cast<unsigned long long *>(h->accum) + (&L == &h->cells ? 0 : 1);
+    A.slow_cap = h->slow_cap;
     A.K = h->K;
     A.npanel = L.npanel;
     A.panel_rows = L.panel_rows;
     A.warps = L.warps;
     A.panels_per_range = L.panels_per_range;
     A.nranges = L.nranges;
+    A.own_range_stride = L.ranked_per_range ? L.n_slots : 0;
+    // plane B of the owner's table and of the streamed table (lanes geometry; 0-sized otherwise)
+    const bool cells_own = &L == &h->cells;
+    A.own_offB = (cells_own ? h->C_pad : h->G_pad) * h->KA;
+    A.oth_offB = (cells_own ? h->G_pad : h->C_pad) * h->KA;
     return A;
 }
 
@@ -270,14 +305,15 @@ int ensure_tables(schpf_engine *h)
     const int K = h->K;
     if (!h->tables_t_valid) {
         CUDA_TRY(cudaMemsetAsync(h->colsum_t_next, 0, sizeof(double) * K, h->stream));
-        RC_TRY(launch_prep_side(h->stream, h->C, K, h->theta_shp, h->theta_rte, h->elog_t, h->Et,
+        RC_TRY(launch_prep_side(h->stream, h->C, K, h->geom_t(), h->theta_shp, h->theta_rte, h->elog_t, h->Et,
                                 h->colsum_t_next));
         h->n_launches += 1;
         h->tables_t_valid = true;
     }
     if (!h->tables_b_valid) {
         CUDA_TRY(cudaMemsetAsync(h->colsum_b, 0, sizeof(double) * K, h->stream));
-        RC_TRY(launch_prep_side(h->stream, h->G, K, h->beta_shp, h->beta_rte, h->elog_b, h->Eb, h->colsum_b));
+        RC_TRY(launch_prep_side(h->stream, h->G, K, h->geom_b(), h->beta_shp, h->beta_rte, h->elog_b, h->Eb,
+                                h->colsum_b));
         h->n_launches += 1;
         h->tables_b_valid = true;
     }
@@ -297,7 +333,7 @@ int require_ready(schpf_engine *h)
 int zero_accumulators(schpf_engine *h, bool genes_too)
 {
     const size_t nt = (size_t)h->C * h->K * 2, nb = (size_t)h->G * h->K * 2;
-    CUDA_TRY(cudaMemsetAsync(h->accum, 0, sizeof(double) * (nt + (genes_too ? nb : 0)), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->accum, 0, sizeof(double) * (ACCUM_HEADER + nt + (genes_too ? nb : 0)), h->stream));
     return SCHPF_OK;
 }
 
@@ -311,7 +347,9 @@ int cells_sweep(schpf_engine *h)
     A.own_elog = h->elog_t;
     A.oth_elog = h->elog_b;
     A.direct = h->direct_t;
-    return timed_sweep(h, SWEEP_SHAPE, h->cells, A);
+    RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->cells, A));
+    h->n_launches += 1;
+    return launch_slow_fixup(h->stream, A, h->overflow);
 }
 
 int genes_sweep(schpf_engine *h)
@@ -324,7 +362,9 @@ int genes_sweep(schpf_engine *h)
     B.own_elog = h->elog_b;
     B.oth_elog = h->elog_t;
     B.direct = h->direct_b;
-    return timed_sweep(h, SWEEP_SHAPE, h->genes, B);
+    RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->genes, B));
+    h->n_launches += 1;
+    return launch_slow_fixup(h->stream, B, h->overflow);
 }
 
 // this shard's beta shape sums + column sums of theta.e_x (theta BEFORE its update,
@@ -332,7 +372,7 @@ int genes_sweep(schpf_engine *h)
 int fold_exchange_buffer(schpf_engine *h)
 {
     const int K = h->K;
-    RC_TRY(launch_fold(h->stream, h->G, K, h->Eb, h->acc_b, h->direct_b, h->exch));
+    RC_TRY(launch_fold(h->stream, h->G, K, h->geom_b(), h->Eb, h->acc_b, h->direct_b, h->exch));
     CUDA_TRY(cudaMemcpyAsync(h->exch + (size_t)h->G * K, h->colsum_t_next, sizeof(double) * K,
                              cudaMemcpyDeviceToDevice, h->stream));
     h->n_launches += 1;
@@ -378,7 +418,7 @@ int step_end_impl(schpf_engine *h, int flags)
         // scHPF_.py:709-714: theta shape from the row sums, rate from xi (old) + column sums of
         // beta.e_x, then xi rate; also next iteration's tables and theta.e_x column sums
         CUDA_TRY(cudaMemsetAsync(h->colsum_t_next, 0, sizeof(double) * K, h->stream));
-        RC_TRY(launch_finalize(h->stream, h->C, K, h->a, h->bp, nullptr, h->Et, h->acc_t, h->direct_t,
+        RC_TRY(launch_finalize(h->stream, h->C, K, h->geom_t(), h->a, h->bp, nullptr, h->Et, h->acc_t, h->direct_t,
                                h->colsum_b, h->xi_shp, h->xi_rte, h->theta_shp, h->theta_rte, h->elog_t,
                                h->Et, h->colsum_t_next));
         h->n_launches += 1;
@@ -387,7 +427,7 @@ int step_end_impl(schpf_engine *h, int flags)
     auto beta_update = [&]() -> int {
         // scHPF_.py:699-704
         CUDA_TRY(cudaMemsetAsync(h->colsum_b, 0, sizeof(double) * K, h->stream));
-        RC_TRY(launch_finalize(h->stream, h->G, K, h->c, h->dp, h->exch, h->Eb, nullptr, nullptr,
+        RC_TRY(launch_finalize(h->stream, h->G, K, h->geom_b(), h->c, h->dp, h->exch, h->Eb, nullptr, nullptr,
                                h->exch + (size_t)h->G * K, h->eta_shp, h->eta_rte, h->beta_shp, h->beta_rte,
                                h->elog_b, h->Eb, h->colsum_b));
         h->n_launches += 1;
@@ -411,6 +451,22 @@ int step_end_impl(schpf_engine *h, int flags)
         RC_TRY(theta_update());
     }
     h->n_iterations += 1;
+    return SCHPF_OK;
+}
+
+// after a synchronisation: did a queue of underflowed nonzeros overflow since the last check?
+int check_overflow(schpf_engine *h)
+{
+    int f = 0;
+    CUDA_TRY(cudaMemcpyAsync(&f, h->overflow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (f) {
+        CUDA_TRY(cudaMemsetAsync(h->overflow, 0, sizeof(int), h->stream));
+        set_error("more than %u nonzeros per sweep underflowed the factored softmax (priors far below 1e-2?): "
+                  "results since the last check are incomplete; use option variant=1 (literal kernel) for this model",
+                  h->slow_cap);
+        return SCHPF_ERR_NUMERIC;
+    }
     return SCHPF_OK;
 }
 
@@ -442,50 +498,82 @@ int finish_coo(schpf_engine *h)
         free_coo(h);
         return SCHPF_ERR_ARG;
     }
+    // sweep family for this K: one lane per owner where it is instantiated, lane pairs otherwise
+    h->lanes = h->opt_lanes && h->opt_variant == 0 && lanes_supported(h->K);
+    if (h->lanes) {
+        const int kp = lanes_kp_of(h->K);
+        h->KB = kp == 20 ? 4 : 0;
+        h->KA = kp - h->KB;
+    } else {
+        h->KA = h->ST;
+        h->KB = 0;
+    }
+    const int TW = h->KA + h->KB;     // doubles per table row
     const int ctas = sweep_ctas_per_sm(h->K);
-    int Po = h->opt_panel_rows > 0 ? h->opt_panel_rows : max_panel_rows(h->K, ctas);
-    const int Pmax = max_panel_rows(h->K, 1);
+    const int Pmax = h->lanes ? lanes_max_panel_rows(h->K) : max_panel_rows(h->K, 1);
+    int Po = h->opt_panel_rows > 0 ? h->opt_panel_rows : h->lanes ? Pmax : max_panel_rows(h->K, ctas);
     if (Po > Pmax) Po = Pmax;
     Po &= ~3;
     if (Po < 4) Po = 4;
     // tables are streamed panel-wise: pad their row counts to whole panels (zero rows)
     const int64_t C_pad = ((h->C + Po - 1) / Po) * Po, G_pad = ((h->G + Po - 1) / Po) * Po;
-    if (C_pad != h->C_pad || !h->Et) {
+    if (C_pad * TW != h->tab_t_elems || !h->Et) {
         dev_free(h->Et);
         dev_free(h->Xt);
-        RC_TRY(dev_alloc(&h->Et, C_pad * h->ST));
-        RC_TRY(dev_alloc(&h->Xt, C_pad * h->ST));
-        h->C_pad = C_pad;
+        RC_TRY(dev_alloc(&h->Et, C_pad * TW));
+        RC_TRY(dev_alloc(&h->Xt, C_pad * TW));
+        h->tab_t_elems = C_pad * TW;
     }
-    if (G_pad != h->G_pad || !h->Eb) {
+    if (G_pad * TW != h->tab_b_elems || !h->Eb) {
         dev_free(h->Eb);
         dev_free(h->Xb);
-        RC_TRY(dev_alloc(&h->Eb, G_pad * h->ST));
-        RC_TRY(dev_alloc(&h->Xb, G_pad * h->ST));
-        h->G_pad = G_pad;
+        RC_TRY(dev_alloc(&h->Eb, G_pad * TW));
+        RC_TRY(dev_alloc(&h->Xb, G_pad * TW));
+        h->tab_b_elems = G_pad * TW;
     }
+    h->C_pad = C_pad;
+    h->G_pad = G_pad;
     // pad rows / pad columns of the streamed tables stay zero for the lifetime of the layout
-    CUDA_TRY(cudaMemsetAsync(h->Et, 0, sizeof(double) * (size_t)C_pad * h->ST, h->stream));
-    CUDA_TRY(cudaMemsetAsync(h->Eb, 0, sizeof(double) * (size_t)G_pad * h->ST, h->stream));
-    CUDA_TRY(cudaMemsetAsync(h->Xt, 0, sizeof(double) * (size_t)C_pad * h->ST, h->stream));
-    CUDA_TRY(cudaMemsetAsync(h->Xb, 0, sizeof(double) * (size_t)G_pad * h->ST, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->Et, 0, sizeof(double) * (size_t)C_pad * TW, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->Eb, 0, sizeof(double) * (size_t)G_pad * TW, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->Xt, 0, sizeof(double) * (size_t)C_pad * TW, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->Xb, 0, sizeof(double) * (size_t)G_pad * TW, h->stream));
     h->tables_t_valid = h->tables_b_valid = false;
 
-    int warps = sweep_default_warps(h->K);
+    int warps = h->lanes ? lanes_default_warps(h->K) : sweep_default_warps(h->K);
     if (h->opt_warps > 0 && h->opt_warps < warps) warps = h->opt_warps;
+    int opw = GROUPS_PER_WARP, lflags = 0;
+    if (h->lanes) {
+        opw = 32;
+        // plane A rows all start at bank group 0: no schedule needed.  Plane B (K 17..20) is either
+        // scheduled (4x4 colouring, pads) or left free with its reads ordered by rotated bank class
+        // (a few conflicts on 2 of the 10 row loads, no pads)
+        const bool free_mode = h->KB == 0 || (h->opt_free_schedule < 0 ? LANES_FREE20_DEFAULT : h->opt_free_schedule != 0);
+        if (free_mode) lflags |= LAYOUT_FREE | (h->KB ? LAYOUT_ROTATE_CLASS : 0);
+        if (!(flag & 16)) lflags |= LAYOUT_YHI;            // every count < 2^21
+        // without a bank schedule the only padding left is the spread of the owners' counts inside a
+        // panel: rank the owners panel by panel (one panel per CTA) and it all but disappears
+        // (measured at K=20 with the plane-B schedule too: 19 % -> 15 % pads, 3.25 -> 3.15 ms per pair)
+        const bool rank = h->opt_rank_per_range < 0 ? true : h->opt_rank_per_range != 0;
+        if (rank) lflags |= LAYOUT_RANK_PER_RANGE | LAYOUT_SINGLE_PANEL_RANGES;
+    }
     trace_mark(h->stream, "validate + tables");
     // 4-byte entries are possible when every count fits 19 bits (flag bit 8 = some count >= 2^19).
     // Measured on cfg-3 they are SLOWER than 8-byte entries (3.61 vs 3.43 ms per sweep pair: the
     // sweep is not HBM-bound and the decode costs issue slots), so they are opt-in: they halve
     // the resident layout (1.8 GB instead of 3.6 GB at 1.9e8 nnz) when memory matters.
-    const bool packed = h->opt_packed_entries && !(flag & 8) && Po <= (1 << PACKED_ROW_BITS);
+    const bool packed = !h->lanes && h->opt_packed_entries && !(flag & 8) && Po <= (1 << PACKED_ROW_BITS);
     RC_TRY(build_side_layout(h->cells, h->stream, h->nnz, h->row, h->col, h->data, h->C, h->G, Po, warps,
-                             h->opt_target_ctas, packed));
+                             h->opt_target_ctas, packed, opw, lflags));
     trace_mark(h->stream, "layout cells total");
     RC_TRY(build_side_layout(h->genes, h->stream, h->nnz, h->col, h->row, h->data, h->G, h->C, Po, warps,
-                             h->opt_target_ctas, packed));
+                             h->opt_target_ctas, packed, opw, lflags));
 
     trace_mark(h->stream, "layout genes total");
+    // room for every nonzero of small matrices, 4 M entries (64 MB per direction) beyond
+    h->slow_cap = (unsigned int)(h->nnz < 1 ? 1 : h->nnz > (1 << 22) ? (1 << 22) : h->nnz);
+    RC_TRY(dev_alloc(&h->slow_q_t, (int64_t)h->slow_cap));
+    RC_TRY(dev_alloc(&h->slow_q_b, (int64_t)h->slow_cap));
     int need = h->cells.nblocks * h->cells.nranges;
     if (need < 1024) need = 1024;
     if (need > h->partials_cap) {
@@ -505,7 +593,7 @@ int finish_coo(schpf_engine *h)
 
 extern "C" {
 
-int schpf_version(void) { return 100; }
+int schpf_version(void) { return 200; }
 
 const char *schpf_last_error(void) { return g_last_error.c_str(); }
 
@@ -560,7 +648,8 @@ int schpf_create(schpf_engine_t **out, int device, int64_t ncells, int64_t ngene
     A(dev_alloc(&h->eta_rte, ngenes));
     A(dev_alloc(&h->elog_t, CK));
     A(dev_alloc(&h->elog_b, GK));
-    A(dev_alloc(&h->accum, 2 * CK + 2 * GK));
+    A(dev_alloc(&h->accum, ACCUM_HEADER + 2 * CK + 2 * GK));
+    A(dev_alloc(&h->overflow, (int64_t)1));
     A(dev_alloc(&h->exch, GK + nfactors));
     A(dev_alloc(&h->colsum_b, (int64_t)nfactors));
     A(dev_alloc(&h->colsum_t_next, (int64_t)nfactors));
@@ -571,11 +660,12 @@ int schpf_create(schpf_engine_t **out, int device, int64_t ncells, int64_t ngene
         schpf_destroy(h);
         return rc;
     }
-    h->acc_t = h->accum;
-    h->direct_t = h->accum + CK;
-    h->acc_b = h->accum + 2 * CK;
-    h->direct_b = h->accum + 2 * CK + GK;
+    h->acc_t = h->accum + ACCUM_HEADER;
+    h->direct_t = h->acc_t + CK;
+    h->acc_b = h->acc_t + 2 * CK;
+    h->direct_b = h->acc_t + 2 * CK + GK;
     cudaMemsetAsync(h->slow_hits, 0, sizeof(unsigned long long), h->stream);
+    cudaMemsetAsync(h->overflow, 0, sizeof(int), h->stream);
     cudaMemsetAsync(h->exch, 0, sizeof(double) * (size_t)(GK + nfactors), h->stream);
     *out = h;
     return SCHPF_OK;
@@ -601,6 +691,7 @@ int schpf_destroy(schpf_engine_t *h)
     dev_free(h->Et); dev_free(h->Eb); dev_free(h->Xt); dev_free(h->Xb); dev_free(h->elog_t); dev_free(h->elog_b);
     dev_free(h->accum); dev_free(h->exch); dev_free(h->colsum_b); dev_free(h->colsum_t_next);
     dev_free(h->partials); dev_free(h->scalars); dev_free(h->slow_hits); dev_free(h->flag);
+    dev_free(h->overflow);
     for (auto &e : h->ev_pool) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -624,6 +715,9 @@ int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value)
     else if (!strcmp(key, "packed_entries")) h->opt_packed_entries = (int)value;
     else if (!strcmp(key, "row_offset")) h->row_offset = value;
     else if (!strcmp(key, "overlap_exchange")) h->opt_overlap_exchange = (int)value;
+    else if (!strcmp(key, "lanes")) h->opt_lanes = (int)value;
+    else if (!strcmp(key, "rank_per_range")) h->opt_rank_per_range = (int)value;
+    else if (!strcmp(key, "free_schedule")) h->opt_free_schedule = (int)value;
     else {
         set_error("unknown option '%s'", key);
         return SCHPF_ERR_ARG;
@@ -732,7 +826,7 @@ int schpf_get_state(schpf_engine_t *h, double *theta_shp, double *theta_rte, dou
     if (eta_shp) RC_TRY(download(eta_shp, h->eta_shp, h->G, h->stream));
     if (eta_rte) RC_TRY(download(eta_rte, h->eta_rte, h->G, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return SCHPF_OK;
+    return check_overflow(h);
 }
 
 int schpf_copy_gene_state(schpf_engine_t *dst, schpf_engine_t *src)
@@ -920,8 +1014,8 @@ int schpf_loss_parts(schpf_engine_t *h, double *sum_llh, int64_t *count)
     RC_TRY(require_ready(h));
     const int K = h->K;
     // e_x tables in the sweep layout (hpf_numba.py:33-41)
-    RC_TRY(launch_ex_table(h->stream, h->C, K, h->theta_shp, h->theta_rte, h->Xt));
-    RC_TRY(launch_ex_table(h->stream, h->G, K, h->beta_shp, h->beta_rte, h->Xb));
+    RC_TRY(launch_ex_table(h->stream, h->C, K, h->geom_t(), h->theta_shp, h->theta_rte, h->Xt));
+    RC_TRY(launch_ex_table(h->stream, h->G, K, h->geom_b(), h->beta_shp, h->beta_rte, h->Xb));
     SweepArgs A = side_args(h, h->cells);
     A.own_tab = h->Xt;
     A.oth_tab = h->Xb;
@@ -946,7 +1040,7 @@ int schpf_loss_parts(schpf_engine_t *h, double *sum_llh, int64_t *count)
     }
     if (sum_llh) *sum_llh = pair[0];
     if (count) *count = (int64_t)(pair[1] + 0.5);
-    return SCHPF_OK;
+    return check_overflow(h);
 }
 
 int schpf_loss(schpf_engine_t *h, double *mean_negative_llh)
@@ -989,6 +1083,29 @@ int schpf_xphi_debug(schpf_engine_t *h, double *out)
     cudaStreamSynchronize(h->stream);
     pool_free(d, h->stream);
     return rc;
+}
+
+int schpf_layout_dump(schpf_engine_t *h, int side, int64_t capacity, int32_t *own, int32_t *oth, int32_t *count,
+                      int64_t *n_out)
+{
+    RC_TRY(check_handle(h));
+    if (!h->have_coo) {
+        set_error("schpf_layout_dump: no matrix");
+        return SCHPF_ERR_STATE;
+    }
+    const SideLayout &L = side == 0 ? h->cells : h->genes;
+    if (n_out) *n_out = L.padded_entries;
+    if (!own || !oth || !count) return SCHPF_OK;       // size query
+    if (capacity < L.padded_entries) {
+        set_error("schpf_layout_dump: buffers hold %lld entries, the layout has %lld", (long long)capacity,
+                  (long long)L.padded_entries);
+        return SCHPF_ERR_ARG;
+    }
+    if (dump_side_layout(L, h->stream, own, oth, count) < 0) {
+        set_error("schpf_layout_dump: device error %s", cudaGetErrorString(cudaGetLastError()));
+        return SCHPF_ERR_CUDA;
+    }
+    return SCHPF_OK;
 }
 
 int schpf_comm_unique_id(char *id128_out)
@@ -1057,16 +1174,20 @@ int schpf_counter(schpf_engine_t *h, const char *what, double *value)
     else if (!strcmp(what, "iterations")) *value = h->n_iterations;
     else if (!strcmp(what, "layout_bytes")) *value = (double)(h->cells.bytes + h->genes.bytes);
     else if (!strcmp(what, "panel_rows")) *value = (double)h->cells.panel_rows;
+    else if (!strcmp(what, "lanes")) *value = h->cells.opw == 32 ? 1.0 : 0.0;
+    else if (!strcmp(what, "warps_per_cta")) *value = (double)h->cells.warps;
     else if (!strcmp(what, "packed_entries")) *value = h->cells.packed ? 1.0 : 0.0;
     else if (!strcmp(what, "grid_cells")) *value = (double)h->cells.nblocks * h->cells.nranges;
     else if (!strcmp(what, "grid_genes")) *value = (double)h->genes.nblocks * h->genes.nranges;
-    else if (!strcmp(what, "sweep_ms")) {
+    else if (!strcmp(what, "shape_sweep_launches")) *value = h->n_shape_sweeps;
+    else if (!strcmp(what, "sweep_ms") || !strcmp(what, "sweep_ms_shape") || !strcmp(what, "sweep_ms_llh")) {
         RC_TRY(collect_timing(h));
-        *value = h->sweep_ms_accum;
+        *value = !strcmp(what, "sweep_ms") ? h->sweep_ms_accum : !strcmp(what, "sweep_ms_shape") ? h->sweep_ms_shape
+                                                                                               : h->sweep_ms_llh;
     } else if (!strcmp(what, "reset")) {
         RC_TRY(collect_timing(h));
-        h->sweep_ms_accum = 0.0;
-        h->n_sweeps = h->n_launches = h->n_iterations = 0;
+        h->sweep_ms_accum = h->sweep_ms_shape = h->sweep_ms_llh = 0.0;
+        h->n_sweeps = h->n_shape_sweeps = h->n_launches = h->n_iterations = 0;
         *value = 0.0;
     } else if (!strcmp(what, "slow_path_hits")) {
         unsigned long long v = 0;

@@ -54,6 +54,46 @@ __global__ void count_owners_kernel(int64_t nnz, const int32_t *__restrict__ own
     if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cnt + key, __popc(peers));
 }
 
+// per-range variant: cnt[range * n_own + owner], range = panel of the other index / panels_per_range
+__global__ void count_owners_ranged_kernel(int64_t nnz, const int32_t *__restrict__ own,
+                                           const int32_t *__restrict__ oth, int panel_rows, int panels_per_range,
+                                           int64_t n_own, int32_t *__restrict__ cnt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const int64_t key = (int64_t)((oth[i] / panel_rows) / panels_per_range) * n_own + own[i];
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cnt + key, __popc(peers));
+}
+
+// sort keys of the per-range ranking: range ascending, count descending (stable: ties keep owner order)
+__global__ void ranged_keys_kernel(int64_t n, int64_t n_own, const int32_t *__restrict__ cnt,
+                                   uint64_t *__restrict__ keys, int32_t *__restrict__ ids)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int64_t range = j / n_own;
+    keys[j] = ((uint64_t)range << 32) | (uint64_t)(0xffffffffu - (uint32_t)cnt[j]);
+    ids[j] = (int32_t)(j - range * n_own);
+}
+
+// slot_of[range][owner], own_id[range][slot] from the per-range sorted order
+__global__ void assign_slots_ranged_kernel(int64_t n_own, int64_t n_slots, int nranges,
+                                           const int32_t *__restrict__ sorted_ids, int32_t *__restrict__ slot_of,
+                                           int32_t *__restrict__ own_id)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_slots * nranges) return;
+    const int64_t range = j / n_slots, s = j - range * n_slots;
+    if (s < n_own) {
+        const int32_t o = sorted_ids[range * n_own + s];
+        own_id[j] = o;
+        slot_of[range * n_own + o] = (int32_t)s;
+    } else {
+        own_id[j] = -1;
+    }
+}
+
 __global__ void iota_kernel(int64_t n, int32_t *p)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,17 +117,21 @@ __global__ void assign_slots_kernel(int64_t n_own, int64_t n_slots, const int32_
 
 __global__ void make_keys_kernel(int64_t nnz, const int32_t *__restrict__ own, const int32_t *__restrict__ oth,
                                  const int32_t *__restrict__ val, const int32_t *__restrict__ slot_of,
-                                 int panel_rows, int npanel, uint64_t *__restrict__ keys,
-                                 uint64_t *__restrict__ vals, int64_t *__restrict__ seg_cnt)
+                                 int panel_rows, int npanel, int64_t ranged_n_own, int panels_per_range, bool free_mode,
+                                 bool rotate, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals, int64_t *__restrict__ seg_cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
-    const int32_t slot = slot_of[own[i]];
     const int32_t t = oth[i];
     const int32_t p = t / panel_rows;
     const int32_t tl = t - p * panel_rows;
+    // ranged_n_own > 0: owners are ranked inside every panel range, slot_of is [nranges][n_own]
+    const int32_t slot = slot_of[(int64_t)(p / panels_per_range) * ranged_n_own + own[i]];
     const int64_t seg = (int64_t)slot * npanel + p;
-    const uint32_t cls = (uint32_t)tl & 3u;
+    // scheduled streams: the bank class of the row.  Free streams keep the owner's nonzeros of a panel
+    // contiguous; `rotate` orders them by bank class, starting at a class that differs between the
+    // four owners of a scheduling group, so that plane-B reads of the group collide less often.
+    const uint32_t cls = !free_mode ? ((uint32_t)tl & 3u) : rotate ? (((uint32_t)tl - (uint32_t)slot) & 3u) : 0u;
     keys[i] = ((uint64_t)seg << (KEY_LOCAL_BITS + KEY_ROT_BITS)) | ((uint64_t)cls << KEY_LOCAL_BITS) |
               (uint64_t)tl;
     vals[i] = ((uint64_t)(uint32_t)val[i] << 32) | (uint64_t)(uint32_t)tl;
@@ -101,7 +145,7 @@ __global__ void make_keys_kernel(int64_t nnz, const int32_t *__restrict__ own, c
 // n[o][c]: nonzeros of owner o (0..3, one per lane pair) whose panel-local row is in
 // bank group c.  Delta = max(row sums, column sums) steps suffice and are necessary.
 __device__ __forceinline__ int qw_delta(const int64_t *__restrict__ cnt4 /* 4 owners x [npanel*4] */,
-                                        int64_t base0, int64_t owner_stride, int n[4][4])
+                                        int64_t base0, int64_t owner_stride, int n[4][4], bool free_mode = false)
 {
     int rs[4] = {0, 0, 0, 0}, cs[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -114,13 +158,13 @@ __device__ __forceinline__ int qw_delta(const int64_t *__restrict__ cnt4 /* 4 ow
         }
     int d = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) d = max(d, max(rs[i], cs[i]));
+    for (int i = 0; i < 4; ++i) d = max(d, free_mode ? rs[i] : max(rs[i], cs[i]));   // free: no bank classes
     return d;
 }
 
 // step pairs per (warp, panel) = ceil(max over the warp's 4 quarter warps of Delta / 2)
-__global__ void warp_steps_kernel(int64_t n_warps, int npanel, const int64_t *__restrict__ cnt4,
-                                  int64_t *__restrict__ pairs)
+__global__ void warp_steps_kernel(int64_t n_warps, int npanel, int opw, bool free_mode,
+                                  const int64_t *__restrict__ cnt4, int64_t *__restrict__ pairs)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_warps * (npanel + 1)) return;
@@ -131,25 +175,43 @@ __global__ void warp_steps_kernel(int64_t n_warps, int npanel, const int64_t *__
         return;
     }
     int m = 0;
-    for (int qw = 0; qw < 4; ++qw) {
+    for (int qw = 0; qw < opw / 4; ++qw) {       // groups of 4 owners scheduled together
         int n[4][4];
-        const int64_t slot0 = wg * GROUPS_PER_WARP + qw * 4;
-        m = max(m, qw_delta(cnt4, (slot0 * npanel + p) * 4, (int64_t)npanel * 4, n));
+        const int64_t slot0 = wg * opw + qw * 4;
+        m = max(m, qw_delta(cnt4, (slot0 * npanel + p) * 4, (int64_t)npanel * 4, n, free_mode));
     }
     pairs[idx] = (m + 1) >> 1;
 }
 
+// position of slot s (0..opw-1 within its warp) in a step row of the stream.  16 owners per warp: the
+// lane pair s.  32 owners per warp: group g = s / 4 of 4 owners scheduled together is the even
+// (g even) or odd lanes of quarter warp g / 2, member m = s % 4 -> lane (g/2)*8 + 2m + (g&1).
+__host__ __device__ __forceinline__ int stream_pos(int s, int opw)
+{
+    if (opw == GROUPS_PER_WARP) return s;
+    const int g = s >> 2, m = s & 3;
+    return (g >> 1) * 8 + 2 * m + (g & 1);
+}
+// and the member index (0..3 inside its scheduling group) of the owner at stream position `pos`
+__host__ __device__ __forceinline__ int pos_member(int pos, int opw)
+{
+    return opw == GROUPS_PER_WARP ? (pos & 3) : ((pos & 7) >> 1);
+}
+
 template <bool PACKED>
-__global__ void fill_pad_kernel(int64_t n_elems, void *entries)
+__global__ void fill_pad_kernel(int64_t n_elems, int opw, bool free_mode, void *entries)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // pads read a real row of the bank group their lane pair would own in an all-pad step
+    // pads read a real row of the bank group their lane (pair) would own in an all-pad step
     // (rows 0..3 are in groups 0..3), so they never conflict with each other
-    const int o = (int)(i % GROUPS_PER_WARP) & 3;
+    const int o = free_mode ? 0 : pos_member((int)(i % opw), opw);
     if (i >= n_elems) return;
     if (PACKED) {
         const int w = (int)pack_entry((uint32_t)o, 0u, true);
         reinterpret_cast<int2 *>(entries)[i] = make_int2(w, w);
+    } else if (opw == 32) {
+        // one-lane stream: the pad flag is bit 31 of the COUNT field, the row is plain (sweep_lanes.cu)
+        reinterpret_cast<int4 *>(entries)[i] = make_int4(o, (int)0x80000000, o, (int)0x80000000);
     } else {
         reinterpret_cast<int4 *>(entries)[i] = make_int4((int)0x80000000 | o, 0, (int)0x80000000 | o, 0);
     }
@@ -165,8 +227,14 @@ __constant__ unsigned char PERM4[24] = {
 // remaining degree equals R must be matched (then the maximum degree drops to R-1); a
 // matching doing so always exists in a bipartite multigraph, and with 4+4 vertices the
 // 24 permutations are simply tried.
+__device__ __forceinline__ int count_field(uint32_t count, bool yhi)
+{
+    return yhi ? __double2hiint((double)count) : (int)count;
+}
+
 template <bool PACKED>
-__global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__restrict__ cnt4,
+__global__ void place_entries_kernel(int64_t n_qw, int npanel, int opw, bool free_mode, bool yhi,
+                                     const int64_t *__restrict__ cnt4,
                                      const int64_t *__restrict__ first4, const uint64_t *__restrict__ vals,
                                      const int64_t *__restrict__ seg_ptr, void *__restrict__ entries_v,
                                      int *__restrict__ unplaced)
@@ -176,12 +244,29 @@ __global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__
     const int64_t qwg = idx / npanel;              // global quarter-warp index
     const int p = (int)(idx - qwg * npanel);
     const int64_t slot0 = qwg * 4;
-    const int64_t wg = slot0 / GROUPS_PER_WARP;
-    const int q0 = (int)(slot0 - wg * GROUPS_PER_WARP);
+    const int64_t wg = slot0 / opw;
+    const int q0 = (int)(slot0 - wg * opw);
     const int64_t base0 = (slot0 * npanel + p) * 4, ostride = (int64_t)npanel * 4;
     int n[4][4], used[4][4];
-    const int delta = qw_delta(cnt4, base0, ostride, n);
+    const int delta = qw_delta(cnt4, base0, ostride, n, free_mode);
     if (delta == 0) return;
+    if (free_mode) {
+        // no bank classes: owner o's nonzeros of this panel in ascending order, one per step
+        const int64_t pair0 = seg_ptr[wg * (npanel + 1) + p];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int64_t src0 = first4[base0 + o * ostride];      // the owner's four class lists are contiguous
+            const int pos = stream_pos(q0 + o, opw);
+            const int cnt_o = n[o][0] + n[o][1] + n[o][2] + n[o][3];
+            for (int step = 0; step < cnt_o; ++step) {
+                const int64_t dst = ((pair0 + (step >> 1)) * opw + pos) * 2 + (step & 1);
+                const uint64_t v = vals[src0 + step];
+                reinterpret_cast<int2 *>(entries_v)[dst] =
+                    make_int2((int)(uint32_t)v, count_field((uint32_t)(v >> 32), yhi));
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int o = 0; o < 4; ++o)
 #pragma unroll
@@ -217,14 +302,15 @@ __global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
             const int c = (pm >> (2 * o)) & 3;
-            const int64_t dst = ((pair0 + (step >> 1)) * GROUPS_PER_WARP + (q0 + o)) * 2 + (step & 1);
+            const int64_t dst = ((pair0 + (step >> 1)) * opw + stream_pos(q0 + o, opw)) * 2 + (step & 1);
             if (n[o][c] > 0) {
                 const int64_t src = first4[base0 + o * ostride + c] + used[o][c];
                 const uint64_t v = vals[src];
                 if (PACKED)
                     reinterpret_cast<uint32_t *>(entries_v)[dst] = pack_entry((uint32_t)v, (uint32_t)(v >> 32), false);
                 else
-                    reinterpret_cast<int2 *>(entries_v)[dst] = make_int2((int)(uint32_t)v, (int)(uint32_t)(v >> 32));
+                    reinterpret_cast<int2 *>(entries_v)[dst] =
+                        make_int2((int)(uint32_t)v, count_field((uint32_t)(v >> 32), yhi));
                 ++used[o][c];
                 --n[o][c];
                 --rs[o];
@@ -233,6 +319,8 @@ __global__ void place_entries_kernel(int64_t n_qw, int npanel, const int64_t *__
                 // idle pair: a pad that reads row c, the bank group this permutation leaves it
                 if (PACKED)
                     reinterpret_cast<uint32_t *>(entries_v)[dst] = pack_entry((uint32_t)c, 0u, true);
+                else if (opw == 32)
+                    reinterpret_cast<int2 *>(entries_v)[dst] = make_int2(c, (int)0x80000000);
                 else
                     reinterpret_cast<int2 *>(entries_v)[dst] = make_int2((int)(0x80000000u | (unsigned)c), 0);
             }
@@ -353,10 +441,24 @@ void SideLayout::release()
 
 int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int32_t *d_own,
                       const int32_t *d_oth, const int32_t *d_val, int64_t n_own, int64_t n_oth,
-                      int panel_rows, int warps, int target_ctas, bool packed)
+                      int panel_rows, int warps, int target_ctas, bool packed, int owners_per_warp, int flags)
 {
     L.release();
+    const int opw = owners_per_warp;
+    const bool free_mode = flags & LAYOUT_FREE, ranked = flags & LAYOUT_RANK_PER_RANGE, yhi = flags & LAYOUT_YHI;
+    if (opw != GROUPS_PER_WARP && opw != 32) {
+        set_error("layout: owners per warp must be 16 or 32, got %d", opw);
+        return SCHPF_ERR_ARG;
+    }
+    if (packed && (opw != GROUPS_PER_WARP || free_mode || yhi)) {
+        set_error("layout: packed entries exist for the lane-pair stream only");
+        return SCHPF_ERR_ARG;
+    }
     L.packed = packed;
+    L.opw = opw;
+    L.free_mode = free_mode;
+    L.ranked_per_range = ranked;
+    L.yhi = yhi;
     if (panel_rows < 4 || panel_rows > (1 << KEY_LOCAL_BITS) || (panel_rows & 3)) {
         set_error("panel_rows must be a multiple of 4 in [4, %d], got %d", 1 << KEY_LOCAL_BITS, panel_rows);
         return SCHPF_ERR_ARG;
@@ -367,12 +469,12 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     L.npanel = (int)((n_oth + panel_rows - 1) / panel_rows);
     if (L.npanel < 1) L.npanel = 1;
     L.warps = warps;
-    const int64_t owners_per_block = (int64_t)warps * GROUPS_PER_WARP;
+    const int64_t owners_per_block = (int64_t)warps * opw;
     L.nblocks = (int)((n_own + owners_per_block - 1) / owners_per_block);
     if (L.nblocks < 1) L.nblocks = 1;
     int nranges = (target_ctas + L.nblocks - 1) / L.nblocks;
     if (nranges < 1) nranges = 1;
-    if (nranges > L.npanel) nranges = L.npanel;
+    if (nranges > L.npanel || (flags & LAYOUT_SINGLE_PANEL_RANGES)) nranges = L.npanel;
     L.panels_per_range = (L.npanel + nranges - 1) / nranges;
     L.nranges = (L.npanel + L.panels_per_range - 1) / L.panels_per_range;
 
@@ -380,13 +482,21 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     const int64_t n_warps = (int64_t)L.nblocks * warps;
     const int64_t n_seg = n_slots * L.npanel * 4;   // (slot, panel, bank group) lists
     const int64_t n_ptr = n_warps * (L.npanel + 1);
+    const int64_t n_rank = ranked ? (int64_t)L.nranges * n_own : n_own;      // ranking problems x owners
+    const int64_t n_ownid = ranked ? (int64_t)L.nranges * n_slots : n_slots;
+    L.n_slots = n_slots;
+    if (n_rank > 0x7fffffffLL) {
+        set_error("layout: %lld (range, owner) pairs exceed the ranking sort", (long long)n_rank);
+        return SCHPF_ERR_ARG;
+    }
 
     L.stream = stream;
-    CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&L.own_id), sizeof(int32_t) * n_slots, stream));
+    CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&L.own_id), sizeof(int32_t) * n_ownid, stream));
     CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&L.seg_ptr), sizeof(int64_t) * n_ptr, stream));
 
     // sizes of the sort / scan work areas first (no device work), then ONE scratch block
     const int key_bits = KEY_LOCAL_BITS + KEY_ROT_BITS + bits_for((uint64_t)(n_seg > 4 ? n_seg / 4 - 1 : 0));
+    const int rank_bits = 32 + bits_for((uint64_t)(L.nranges > 1 ? L.nranges - 1 : 0));
     size_t tmp_bytes = 0, need = 0;
     {
         cub::DoubleBuffer<int32_t> k32(nullptr, nullptr), v32(nullptr, nullptr);
@@ -395,20 +505,26 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
         cub::DoubleBuffer<uint64_t> k64(nullptr, nullptr), v64(nullptr, nullptr);
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, k64, v64, nnz, 0, key_bits, stream));
         if (need > tmp_bytes) tmp_bytes = need;
+        if (ranked) {
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, k64, v32, (int)n_rank, 0, rank_bits, stream));
+            if (need > tmp_bytes) tmp_bytes = need;
+        }
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, (int64_t *)nullptr, (int64_t *)nullptr, n_seg, stream));
         if (need > tmp_bytes) tmp_bytes = need;
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, (int64_t *)nullptr, (int64_t *)nullptr, n_ptr, stream));
         if (need > tmp_bytes) tmp_bytes = need;
     }
     const size_t R = 256;   // Scratch::take rounds every piece up to this
-    const size_t total = 5 * (sizeof(int32_t) * n_own + R) + 2 * (sizeof(int64_t) * n_seg + R) +
-                         (sizeof(int64_t) * n_ptr + R) + 4 * (sizeof(uint64_t) * nnz + R) + (tmp_bytes + R) + 2 * R;
+    const size_t total = 5 * (sizeof(int32_t) * n_rank + R) + 2 * (sizeof(uint64_t) * (ranked ? n_rank : 0) + R) +
+                         2 * (sizeof(int64_t) * n_seg + R) + (sizeof(int64_t) * n_ptr + R) +
+                         4 * (sizeof(uint64_t) * nnz + R) + (tmp_bytes + R) + 2 * R;
     Scratch scratch;
     CUDA_TRY(scratch.acquire(total, stream));
     int *unplaced = scratch.take<int>(1);
-    int32_t *cnt = scratch.take<int32_t>(n_own), *ids = scratch.take<int32_t>(n_own);
-    int32_t *cnt_alt = scratch.take<int32_t>(n_own), *ids_alt = scratch.take<int32_t>(n_own);
-    int32_t *slot_of = scratch.take<int32_t>(n_own);
+    int32_t *cnt = scratch.take<int32_t>(n_rank), *ids = scratch.take<int32_t>(n_rank);
+    int32_t *cnt_alt = scratch.take<int32_t>(n_rank), *ids_alt = scratch.take<int32_t>(n_rank);
+    int32_t *slot_of = scratch.take<int32_t>(n_rank);
+    uint64_t *rkeys = scratch.take<uint64_t>(ranked ? n_rank : 0), *rkeys_alt = scratch.take<uint64_t>(ranked ? n_rank : 0);
     int64_t *seg_cnt = scratch.take<int64_t>(n_seg), *seg_first = scratch.take<int64_t>(n_seg);
     int64_t *pairs = scratch.take<int64_t>(n_ptr);
     uint64_t *keys = scratch.take<uint64_t>(nnz), *vals = scratch.take<uint64_t>(nnz);
@@ -421,14 +537,28 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     CUDA_TRY(cudaMemsetAsync(unplaced, 0, sizeof(int), stream));
 
     trace_mark(stream, "  alloc");
-    // 1. owners ranked by nonzero count, descending (stable: ties keep index order)
-    CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * n_own, stream));
-    if (nnz > 0) count_owners_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(nnz, d_own, cnt);
-    iota_kernel<<<blocks_for(n_own, 256), 256, 0, stream>>>(n_own, ids);
-    cub::DoubleBuffer<int32_t> cnt_db(cnt, cnt_alt), ids_db(ids, ids_alt);
-    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, cnt_db, ids_db, (int)n_own, 0, 32, stream));
-    assign_slots_kernel<<<blocks_for(n_slots, 256), 256, 0, stream>>>(n_own, n_slots, ids_db.Current(), slot_of,
-                                                                     L.own_id);
+    // 1. owners ranked by nonzero count, descending (stable: ties keep index order) -- over the whole
+    //    other axis, or (ranked) separately inside every panel range
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * n_rank, stream));
+    if (!ranked) {
+        if (nnz > 0) count_owners_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(nnz, d_own, cnt);
+        iota_kernel<<<blocks_for(n_own, 256), 256, 0, stream>>>(n_own, ids);
+        cub::DoubleBuffer<int32_t> cnt_db(cnt, cnt_alt), ids_db(ids, ids_alt);
+        CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, cnt_db, ids_db, (int)n_own, 0, 32, stream));
+        assign_slots_kernel<<<blocks_for(n_slots, 256), 256, 0, stream>>>(n_own, n_slots, ids_db.Current(), slot_of,
+                                                                         L.own_id);
+    } else {
+        if (nnz > 0)
+            count_owners_ranged_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(nnz, d_own, d_oth, panel_rows,
+                                                                                L.panels_per_range, n_own, cnt);
+        ranged_keys_kernel<<<blocks_for(n_rank, 256), 256, 0, stream>>>(n_rank, n_own, cnt, rkeys, ids);
+        cub::DoubleBuffer<uint64_t> rk_db(rkeys, rkeys_alt);
+        cub::DoubleBuffer<int32_t> ids_db(ids, ids_alt);
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, rk_db, ids_db, (int)n_rank, 0, rank_bits, stream));
+        assign_slots_ranged_kernel<<<blocks_for(n_ownid, 256), 256, 0, stream>>>(n_own, n_slots, L.nranges,
+                                                                                ids_db.Current(), slot_of, L.own_id);
+    }
+    CUDA_TRY(cudaGetLastError());
 
     trace_mark(stream, "  owner ranking");
     // 2. sort keys (slot, panel, bank group, local index) and per-list counts
@@ -436,7 +566,9 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     const uint64_t *vals_sorted = vals;
     if (nnz > 0) {
         make_keys_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(nnz, d_own, d_oth, d_val, slot_of, panel_rows,
-                                                                  L.npanel, keys, vals, seg_cnt);
+                                                                  L.npanel, ranked ? n_own : 0, L.panels_per_range,
+                                                                  free_mode, (flags & LAYOUT_ROTATE_CLASS) != 0, keys, vals,
+                                                                  seg_cnt);
         trace_mark(stream, "  keys + counts");
         // both buffers of a pair are ours, so the sort ping-pongs between them (O(1) extra storage)
         cub::DoubleBuffer<uint64_t> keys_db(keys, keys_alt), vals_db(vals, vals_alt);
@@ -447,32 +579,32 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, seg_cnt, seg_first, n_seg, stream));
 
     // 3. padded lengths per (warp, panel) and their prefix sum
-    warp_steps_kernel<<<blocks_for(n_ptr, 256), 256, 0, stream>>>(n_warps, L.npanel, seg_cnt, pairs);
+    warp_steps_kernel<<<blocks_for(n_ptr, 256), 256, 0, stream>>>(n_warps, L.npanel, opw, free_mode, seg_cnt, pairs);
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pairs, L.seg_ptr, n_ptr, stream));
     int64_t total_pairs = 0;
     CUDA_TRY(cudaMemcpyAsync(&total_pairs, L.seg_ptr + (n_ptr - 1), sizeof(int64_t), cudaMemcpyDeviceToHost,
                              stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     L.total_pairs = total_pairs;   // last column of every warp row is 0, so the last prefix is the total
-    L.padded_entries = total_pairs * 2 * GROUPS_PER_WARP;
+    L.padded_entries = total_pairs * 2 * opw;
 
     trace_mark(stream, "  scans + lengths");
     // 4. entry stream
-    const int64_t n_elems = total_pairs * GROUPS_PER_WARP;      // one element = two steps of a lane pair
+    const int64_t n_elems = total_pairs * opw;      // one element = two steps of a lane (pair)
     const size_t elem_bytes = packed ? sizeof(int2) : sizeof(int4);
     CUDA_TRY(pool_malloc(&L.entries, elem_bytes * (n_elems > 0 ? n_elems : 1), stream));
     if (n_elems > 0) {
-        if (packed) fill_pad_kernel<true><<<blocks_for(n_elems, 256), 256, 0, stream>>>(n_elems, L.entries);
-        else fill_pad_kernel<false><<<blocks_for(n_elems, 256), 256, 0, stream>>>(n_elems, L.entries);
+        if (packed) fill_pad_kernel<true><<<blocks_for(n_elems, 256), 256, 0, stream>>>(n_elems, opw, free_mode, L.entries);
+        else fill_pad_kernel<false><<<blocks_for(n_elems, 256), 256, 0, stream>>>(n_elems, opw, free_mode, L.entries);
     }
     if (nnz > 0) {
         const int64_t n_qw = n_slots / 4;
         if (packed)
             place_entries_kernel<true><<<blocks_for(n_qw * L.npanel, 128), 128, 0, stream>>>(
-                n_qw, L.npanel, seg_cnt, seg_first, vals_sorted, L.seg_ptr, L.entries, unplaced);
+                n_qw, L.npanel, opw, free_mode, yhi, seg_cnt, seg_first, vals_sorted, L.seg_ptr, L.entries, unplaced);
         else
             place_entries_kernel<false><<<blocks_for(n_qw * L.npanel, 128), 128, 0, stream>>>(
-                n_qw, L.npanel, seg_cnt, seg_first, vals_sorted, L.seg_ptr, L.entries, unplaced);
+                n_qw, L.npanel, opw, free_mode, yhi, seg_cnt, seg_first, vals_sorted, L.seg_ptr, L.entries, unplaced);
     }
     CUDA_TRY(cudaGetLastError());
     trace_mark(stream, "  schedule + place");
@@ -484,8 +616,74 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
         L.release();
         return SCHPF_ERR_STATE;
     }
-    L.bytes = sizeof(int32_t) * n_slots + sizeof(int64_t) * n_ptr + elem_bytes * n_elems;
+    L.bytes = sizeof(int32_t) * n_ownid + sizeof(int64_t) * n_ptr + elem_bytes * n_elems;
     return SCHPF_OK;
+}
+
+// ---- debug dump: the stream decoded back to triples (tests: exact integer round trip) -------------
+namespace {
+template <bool PACKED>
+__global__ void dump_entries_kernel(int64_t n_warps, int npanel, int opw, int panel_rows, int panels_per_range,
+                                    int64_t own_range_stride, bool yhi, const int32_t *__restrict__ own_id,
+                                    const int64_t *__restrict__ seg_ptr, const void *__restrict__ entries_v,
+                                    int32_t *__restrict__ own, int32_t *__restrict__ oth, int32_t *__restrict__ cnt)
+{
+    // one thread per (warp, panel)
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_warps * npanel) return;
+    const int64_t wg = idx / npanel;
+    const int p = (int)(idx - wg * npanel);
+    const int64_t i0 = seg_ptr[wg * (npanel + 1) + p], i1 = seg_ptr[wg * (npanel + 1) + p + 1];
+    const int64_t range = p / panels_per_range;
+    for (int64_t i = i0; i < i1; ++i)
+        for (int s = 0; s < opw; ++s) {
+            const int pos = stream_pos(s, opw);
+            const int32_t o = own_id[range * own_range_stride + wg * opw + s];
+            for (int e = 0; e < 2; ++e) {
+                const int64_t at = (i * opw + pos) * 2 + e;
+                int rowf, field;
+                bool pad;
+                if (PACKED) {
+                    const uint32_t w = reinterpret_cast<const uint32_t *>(entries_v)[at];
+                    pad = w >> 31;
+                    rowf = (int)(w & ((1u << PACKED_ROW_BITS) - 1));
+                    field = (int)((w >> PACKED_ROW_BITS) & ((1u << PACKED_COUNT_BITS) - 1));
+                } else {
+                    const int2 v = reinterpret_cast<const int2 *>(entries_v)[at];
+                    pad = opw == 32 ? v.y < 0 : v.x < 0;
+                    rowf = v.x & 0x7fffffff;
+                    field = v.y & 0x7fffffff;
+                }
+                const int c = yhi ? (int)__hiloint2double(field, 0) : field;
+                own[at] = pad ? -1 : o;
+                oth[at] = pad ? -1 : p * panel_rows + rowf;
+                cnt[at] = pad ? 0 : c;
+            }
+        }
+}
+}  // namespace
+
+int64_t dump_side_layout(const SideLayout &L, cudaStream_t stream, int32_t *own, int32_t *oth, int32_t *cnt)
+{
+    const int64_t n = L.padded_entries;
+    if (n <= 0) return 0;
+    int32_t *d = nullptr;
+    if (pool_malloc(reinterpret_cast<void **>(&d), sizeof(int32_t) * 3 * n, stream) != cudaSuccess) return -1;
+    const int64_t n_warps = (int64_t)L.nblocks * L.warps;
+    const int64_t stride = L.ranked_per_range ? L.n_slots : 0;
+    const int blocks = (int)((n_warps * L.npanel + 127) / 128);
+    if (L.packed)
+        dump_entries_kernel<true><<<blocks, 128, 0, stream>>>(n_warps, L.npanel, L.opw, L.panel_rows, L.panels_per_range,
+                                                              stride, L.yhi, L.own_id, L.seg_ptr, L.entries, d, d + n, d + 2 * n);
+    else
+        dump_entries_kernel<false><<<blocks, 128, 0, stream>>>(n_warps, L.npanel, L.opw, L.panel_rows, L.panels_per_range,
+                                                               stride, L.yhi, L.own_id, L.seg_ptr, L.entries, d, d + n, d + 2 * n);
+    cudaMemcpyAsync(own, d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(oth, d + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(cnt, d + 2 * n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, stream);
+    const cudaError_t e = cudaStreamSynchronize(stream);
+    pool_free(d, stream);
+    return e == cudaSuccess ? n : -1;
 }
 
 }  // namespace schpf

@@ -108,8 +108,9 @@ int schpf_compute_Xphi_data(int device, int64_t nnz, int64_t ncells, int64_t nge
     RC_TRY(S.alloc(&Et, ncells * ST));
     RC_TRY(S.alloc(&Eb, ngenes * ST));
     RC_TRY(S.alloc(&xphi, nnz * K));
-    RC_TRY(launch_prep_side(nullptr, ncells, K, ts, tr, elt, Et, nullptr));
-    RC_TRY(launch_prep_side(nullptr, ngenes, K, bs, br, elb, Eb, nullptr));
+    const TabGeom tg = {ST, 0, 0};
+    RC_TRY(launch_prep_side(nullptr, ncells, K, tg, ts, tr, elt, Et, nullptr));
+    RC_TRY(launch_prep_side(nullptr, ngenes, K, tg, bs, br, elb, Eb, nullptr));
     RC_TRY(launch_literal(nullptr, nnz, K, d_row, d_col, d_data, elt, elb, xphi, nullptr, nullptr));
     return get(Xphi_out, xphi, nnz * K);
 }

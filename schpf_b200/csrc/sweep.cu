@@ -289,31 +289,13 @@ sweep_kernel(const SweepArgs A)
             }
 #endif
             if (MODE == SWEEP_SHAPE) {
-                if (slow && own >= 0) {
-                    // log-space redo of an underflowed nonzero (hpf_numba.py:98-112); both lanes of
-                    // the pair get here together.  Rare: kept rolled, costs the hot path no registers.
-                    const int K = A.K;
+                if (slow && own >= 0 && h == 0) {
+                    // underflowed nonzeros are redone in log space (hpf_numba.py:98-112) by
+                    // slow_fixup_kernel after the sweep; one lane of the pair queues them
 #pragma unroll
-                    for (int e = 0; e < NS; ++e) {
-                        if (s[e] > TINY_NORMALIZER || ey[e] == 0) continue;
-                        const double y = (double)ey[e];
-                        const double *eo = A.own_elog + (int64_t)own * K;
-                        const double *et = A.oth_elog + ((int64_t)p * A.panel_rows + ex[e]) * K;
-                        double largest = -INFINITY, normalizer = 0.0;
-#pragma unroll 1
-                        for (int k = 0; k < K; ++k) largest = fmax(largest, eo[k] + et[k]);
-#pragma unroll 1
-                        for (int k = 0; k < K; ++k) normalizer += exp(eo[k] + et[k] - largest);
-#pragma unroll 1
-                        for (int k = 2 * h; k < K; k += 4) {
-                            atomicAdd(A.direct + (int64_t)own * K + k,
-                                      y * exp(eo[k] + et[k] - largest) / normalizer);
-                            if (k + 1 < K)
-                                atomicAdd(A.direct + (int64_t)own * K + k + 1,
-                                          y * exp(eo[k + 1] + et[k + 1] - largest) / normalizer);
-                        }
-                        if (h == 0) atomicAdd(A.slow_hits, 1ULL);
-                    }
+                    for (int e = 0; e < NS; ++e)
+                        if (!(s[e] > TINY_NORMALIZER) && ey[e] != 0)
+                            slow_enqueue(A, own, p * A.panel_rows + ex[e], (double)ey[e]);
                 }
             } else {
                 // hpf_numba.py:49-50 without the lgamma term (a constant of the data).  Both lanes of

@@ -211,6 +211,18 @@ class CaviEngine(object):
         _lib.check(self._lib.schpf_xphi_debug(self._h, dptr(out)))
         return out
 
+    def layout_dump(self, side):
+        """The device layout of one sweep direction (0: cells own, 1: genes own) decoded back to
+        triples in stream order: (owner, other, count) int32 arrays, pads as (-1, -1, 0)."""
+        n = c_i64()
+        _lib.check(self._lib.schpf_layout_dump(self._h, c_int(int(side)), c_i64(0), None, None, None,
+                                               ctypes.byref(n)))
+        own, oth, cnt = (np.empty(n.value, dtype=np.int32) for _ in range(3))
+        if n.value:
+            _lib.check(self._lib.schpf_layout_dump(self._h, c_int(int(side)), n, _lib.iptr(own), _lib.iptr(oth),
+                                                   _lib.iptr(cnt), ctypes.byref(n)))
+        return own, oth, cnt
+
     def synchronize(self):
         _lib.check(self._lib.schpf_synchronize(self._h))
 

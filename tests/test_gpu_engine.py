@@ -478,14 +478,14 @@ def test_run_trials_reproduces_the_reference(g_trials, capsys):
 
 
 def test_packed_and_wide_entry_streams_agree():
-    """The opt-in 4-byte stream format (row | count<<12 | pad<<31) needs all counts below 2^19;
-    otherwise the 8-byte format is kept.  Same numbers either way."""
+    """The opt-in 4-byte stream format (row | count<<12 | pad<<31) of the lane-pair kernels needs all
+    counts below 2^19; otherwise the 8-byte format is kept.  Same numbers either way."""
     row, col, data, st = _random_problem(350, 500, 20, 25000, 17)
     big = data.copy()
     big[7] = (1 << 19) + 5                      # does not fit the packed format
     results = {}
-    for name, d, opts in (("packed", data, {"packed_entries": 1}), ("wide", data, {}),
-                          ("auto_wide", big, {"packed_entries": 1})):
+    for name, d, opts in (("packed", data, {"packed_entries": 1, "lanes": 0}), ("wide", data, {"lanes": 0}),
+                          ("auto_wide", big, {"packed_entries": 1, "lanes": 0})):
         with CaviEngine(350, 500, 20, **opts) as e:
             e.set_coo(row, col, d)
             e.set_hyper(0.3, 1.0, 0.7, 0.3, 1.0, 1.3)
