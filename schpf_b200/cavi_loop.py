@@ -20,9 +20,10 @@ HOST_DIRICHLET_LIMIT = 1 << 24
 # distinct windows is at most this; beyond, one engine is re-laid out every iteration
 MINIBATCH_ENGINE_CACHE = 64
 
-# theta / xi of all cells on the device between minibatch iterations (see MinibatchLoop).
-# Opt-in: the host logic is covered by the CPU tests, the copies have not run on hardware yet.
-MINIBATCH_DEVICE_STATE = False
+# theta / xi of all cells stay on the device between minibatch iterations (see MinibatchLoop);
+# False keeps them in host arrays (a batch then moves 4*batchsize*K doubles over PCIe per iteration).
+# Both modes reproduce the reference's seeded minibatch runs (tests/test_gpu_minibatch.py).
+MINIBATCH_DEVICE_STATE = True
 
 
 class MinibatchSchedule(object):
@@ -31,16 +32,16 @@ class MinibatchSchedule(object):
     around the end.  `next()` returns (window start, cell indices); `order` is the shuffled
     cell order (None until the first draw, like the reference's lazy generator)."""
 
-    def __init__(self, ncells, batchsize):
+    def __init__(self, ncells, batchsize, rng=np.random):
         assert ncells >= batchsize
         self.ncells, self.batchsize = int(ncells), int(batchsize)
-        self.order, self._start = None, 0
+        self.order, self._start, self.rng = None, 0, rng
         self._offsets = np.arange(self.batchsize)
 
     def draw_order(self):
         if self.order is None:
             self.order = np.arange(self.ncells)
-            np.random.shuffle(self.order)
+            self.rng.shuffle(self.order)
         return self.order
 
     def next(self):
@@ -62,28 +63,28 @@ def minibatch_windows(ncells, batchsize):
         yield sched.next()
 
 
-def _random_phi_step(engine, data, nfactors, **flags):
+def _random_phi_step(engine, data, nfactors, rng=np.random, **flags):
     """First iteration from y * Dirichlet(1_K) instead of the E-step (scHPF_.py:652-655):
     numpy's stream while the draw is small enough to make on the host, the device's
     counter-based generator (seeded from numpy's stream) beyond."""
     nnz = data.shape[0]
     if nnz * nfactors <= HOST_DIRICHLET_LIMIT:
-        random_phi = np.random.dirichlet(np.ones(nfactors), nnz)
+        random_phi = rng.dirichlet(np.ones(nfactors), nnz)
         engine.step_with_xphi(data[:, None] * random_phi, **flags)
     else:
-        engine.step_random_phi(int(np.random.randint(0, 2 ** 31 - 1)), **flags)
+        engine.step_random_phi(int(rng.randint(0, 2 ** 31 - 1)), **flags)
 
 
 class FullBatchLoop(object):
     """All cells every iteration; with `process_group`, this rank's shard of the cells."""
 
     def __init__(self, new_engine, X, hyper, state, nfactors, freeze_genes, simultaneous,
-                 process_group=None, shared_seed=None):
-        self.X, self.nfactors = X, nfactors
+                 process_group=None, shared_seed=None, rng=np.random, engine_options=None):
+        self.X, self.nfactors, self.rng = X, nfactors, rng
         self.flags = dict(freeze_genes=freeze_genes, simultaneous=simultaneous)
         self.freeze_genes = freeze_genes
         self.process_group, self.shared_seed = process_group, shared_seed
-        self.engine = new_engine(*X.shape)
+        self.engine = new_engine(*X.shape, **(engine_options or {}))
         if process_group is not None:
             from .engine import ShardedEngine
             self.engine = ShardedEngine(self.engine, process_group)
@@ -99,15 +100,20 @@ class FullBatchLoop(object):
         """iterations t .. t+n-1"""
         if n > 0 and t == 0 and reinit:
             if self.process_group is not None:
-                self.engine.step(1, random_phi_seed=self.shared_seed(self.process_group), **self.flags)
+                self.engine.step(1, random_phi_seed=self.shared_seed(self.process_group, self.rng), **self.flags)
             else:
-                _random_phi_step(self.engine, self.X.data, self.nfactors, **self.flags)
+                _random_phi_step(self.engine, self.X.data, self.nfactors, self.rng, **self.flags)
             n -= 1
         if n > 0:
             self.engine.step(n, **self.flags)
 
     def loss(self):
         return self.engine.loss()
+
+    def gene_state_engine(self):
+        """The device engine holding the newest beta / eta (None when the engine is not a CaviEngine)."""
+        eng = getattr(self.engine, "local", self.engine)
+        return eng if hasattr(eng, "copy_gene_state_from") else None
 
     def host_state(self):
         """{name: (vi_shape, vi_rate)}; the gene side is absent when it is frozen"""
@@ -144,7 +150,8 @@ class MinibatchLoop(object):
     """
 
     def __init__(self, new_engine, X, hyper, state, nfactors, batchsize, freeze_genes, simultaneous,
-                 device_state=None):
+                 device_state=None, rng=np.random):
+        self.rng = rng
         self.new_engine, self.hyper, self.nfactors = new_engine, hyper, nfactors
         self.ncells, self.ngenes = X.shape
         self.batchsize = int(batchsize)
@@ -157,7 +164,7 @@ class MinibatchLoop(object):
         f = lambda pair: [np.array(pair[0], dtype=np.float64, copy=True), np.array(pair[1], dtype=np.float64, copy=True)]
         self.theta, self.xi = f(state["theta"]), f(state["xi"])      # host mode: the live copy
         self._gene_init = dict(beta=state["beta"], eta=state["eta"])
-        self.schedule = MinibatchSchedule(self.ncells, self.batchsize)
+        self.schedule = MinibatchSchedule(self.ncells, self.batchsize, rng)
         n_windows = self.ncells // gcd(self.ncells, self.batchsize)
         self.cache_engines = n_windows <= MINIBATCH_ENGINE_CACHE
         self.engines = {}          # window start -> engine (only one entry when not caching)
@@ -222,7 +229,7 @@ class MinibatchLoop(object):
             if tt == 0 and reinit:
                 if Xb is None:
                     Xb = self._batch_coo(start, batch_ix)
-                _random_phi_step(eng, Xb.data, self.nfactors, **self.flags)
+                _random_phi_step(eng, Xb.data, self.nfactors, self.rng, **self.flags)
             else:
                 eng.step(1, **self.flags)
             if self.device_state:
@@ -249,6 +256,10 @@ class MinibatchLoop(object):
         else:
             full.copy_gene_state_from(self.current)
         return full.loss()
+
+    def gene_state_engine(self):
+        eng = self.current
+        return eng if eng is not None and hasattr(eng, "copy_gene_state_from") else None
 
     def host_state(self):
         if self.device_state and self.full is not None:

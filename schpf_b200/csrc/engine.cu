@@ -192,7 +192,7 @@ struct schpf_engine {
 namespace {
 
 #ifndef LANES_FREE20_DEFAULT
-#define LANES_FREE20_DEFAULT 0
+#define LANES_FREE20_DEFAULT 1
 #endif
 constexpr int64_t ACCUM_HEADER = 16;   // doubles in front of the accumulators: the two queue counters
 

@@ -52,10 +52,19 @@ namespace {
 #ifndef LANES_BULK_RED
 #define LANES_BULK_RED 1
 #endif
+#ifndef LANES_CTAS
+#define LANES_CTAS 1      // CTAs per SM: 2 = half the warps and half the panel each (fills and epilogues of one hide behind the other)
+#endif
 // measurement-only builds (never shipped): 1 = row loads without the arithmetic, 2 = arithmetic
 // without the row loads -- how much of the sweep is LSU time, how much fp64 time, how much overlaps
 #ifndef LANES_EXP
 #define LANES_EXP 0
+#endif
+#ifndef LANES_PREFETCH
+#define LANES_PREFETCH 1  // 1: next trip's stream elements requested at the top of a trip; 0: reloaded after last use
+#endif
+#ifndef LANES_L2_AHEAD
+#define LANES_L2_AHEAD 8  // trips ahead of which the stream lines are asked into L2
 #endif
 
 struct Steps1 { static constexpr int value = 1; };
@@ -64,7 +73,7 @@ struct Steps2 { static constexpr int value = 2; };
 template <int NA, int REM>
 struct LaneCfg {
     static constexpr int KA = 16 * NA, KB = 4 * REM, KP = KA + KB;
-    static constexpr int WARPS = KP <= 16 ? LANES_W16 : KP <= 20 ? LANES_W20 : LANES_W32;
+    static constexpr int WARPS = (KP <= 16 ? LANES_W16 : KP <= 20 ? LANES_W20 : LANES_W32) / LANES_CTAS;
     static constexpr int NS = KP <= 16 ? LANES_NS16 : KP <= 20 ? LANES_NS20 : LANES_NS32;
 };
 
@@ -92,7 +101,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 }
 
 template <int NA, int REM, int MODE, bool YHI>
-__global__ void __launch_bounds__(LaneCfg<NA, REM>::WARPS * 32, 1)
+__global__ void __launch_bounds__(LaneCfg<NA, REM>::WARPS * 32, LANES_CTAS)
 lane_sweep_kernel(const SweepArgs A)
 {
     using Cfg = LaneCfg<NA, REM>;
@@ -265,12 +274,16 @@ lane_sweep_kernel(const SweepArgs A)
         mbar_wait(mbar, parity);
         parity ^= 1u;
 
-        // Two stream elements per trip, each in its own registers; an element is reloaded right
-        // after its last use, i.e. one block ahead of its next use, and the line it comes from was
-        // asked into L2 eight trips earlier.
+        // Two stream elements per trip.  The elements of the NEXT trip are requested before this
+        // trip's arithmetic starts (a whole trip = four steps of latency cover), and the lines of the
+        // trip LANES_L2_AHEAD ahead are asked into L2.
         int j = 0;
         for (; j + 1 < n; j += 2, ptr += 64) {
-            prefetch_l2(ptr + 8 * 64);
+            prefetch_l2(ptr + LANES_L2_AHEAD * 64);            // immediate offsets from the lane's own pointer:
+            prefetch_l2(ptr + LANES_L2_AHEAD * 64 + 32);       // no predicate, no extra registers
+#if LANES_PREFETCH == 0
+            // variant: an element is reloaded right after its last use (no copies, two steps of
+            // cover: enough for an L2 hit, which the prefetch above is there to make it)
             if constexpr (Cfg::NS == 2) {
                 {
                     const int ex[2] = {cur.x, cur.z}, ey[2] = {cur.y, cur.w};
@@ -282,25 +295,38 @@ lane_sweep_kernel(const SweepArgs A)
                     process(Steps2{}, ex, ey, oth0);
                 }
                 if (j + 3 < n) nxt = ld_stream_int4(ptr + 96);
+                continue;
+            }
+#endif
+            const int4 c0 = cur, c1 = nxt;
+            if (j + 2 < n) cur = ld_stream_int4(ptr + 64);
+            if (j + 3 < n) nxt = ld_stream_int4(ptr + 96);
+            if constexpr (Cfg::NS == 2) {
+                {
+                    const int ex[2] = {c0.x, c0.z}, ey[2] = {c0.y, c0.w};
+                    process(Steps2{}, ex, ey, oth0);
+                }
+                {
+                    const int ex[2] = {c1.x, c1.z}, ey[2] = {c1.y, c1.w};
+                    process(Steps2{}, ex, ey, oth0);
+                }
             } else {
                 {
-                    const int ex[1] = {cur.x}, ey[1] = {cur.y};
+                    const int ex[1] = {c0.x}, ey[1] = {c0.y};
                     process(Steps1{}, ex, ey, oth0);
                 }
                 {
-                    const int ex[1] = {cur.z}, ey[1] = {cur.w};
-                    process(Steps1{}, ex, ey, oth0);
-                }
-                if (j + 2 < n) cur = ld_stream_int4(ptr + 64);
-                {
-                    const int ex[1] = {nxt.x}, ey[1] = {nxt.y};
+                    const int ex[1] = {c0.z}, ey[1] = {c0.w};
                     process(Steps1{}, ex, ey, oth0);
                 }
                 {
-                    const int ex[1] = {nxt.z}, ey[1] = {nxt.w};
+                    const int ex[1] = {c1.x}, ey[1] = {c1.y};
                     process(Steps1{}, ex, ey, oth0);
                 }
-                if (j + 3 < n) nxt = ld_stream_int4(ptr + 96);
+                {
+                    const int ex[1] = {c1.z}, ey[1] = {c1.w};
+                    process(Steps1{}, ex, ey, oth0);
+                }
             }
         }
         if (j < n) {
@@ -441,14 +467,14 @@ bool lanes_supported(int K)
 int lanes_default_warps(int K)
 {
     const int kp = lanes_kp_of(K);
-    return kp <= 16 ? LANES_W16 : kp <= 20 ? LANES_W20 : LANES_W32;
+    return (kp <= 16 ? LANES_W16 : kp <= 20 ? LANES_W20 : LANES_W32) / LANES_CTAS;
 }
 
 // rows of the other axis per panel: the whole shared memory of an SM (one CTA per SM)
 int lanes_max_panel_rows(int K)
 {
     const int kp = lanes_kp_of(K);
-    const size_t budget = (size_t)(228 * 1024) - 1024 - 256;
+    const size_t budget = (size_t)(228 * 1024) / LANES_CTAS - 1024 - 256;
     int rows = (int)(budget / ((size_t)kp * 8));
     rows &= ~3;
     if (rows > 4096) rows = 4096;   // 12-bit local index in the sort key

@@ -27,18 +27,41 @@ _engine_factory = None
 
 
 # ---- helpers for cell-sharded fits (torch.distributed; any backend) ----------------
-def _dist_device(group):
+def _dist_device(group, device=None):
+    """Where collective operands live: the model's own CUDA device on NCCL groups (not whatever
+    torch's current device happens to be), the host otherwise."""
     import torch
     import torch.distributed as dist
-    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    if dist.get_backend(group) != "nccl":
+        return torch.device("cpu")
+    return torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
 
 
-def _global_mean_var_ratio(group, local_sums, sharded_axis):
+def _global_row_offset(group, ncells, device=None):
+    """Index of this rank's first cell in the rank-ordered concatenation of all shards."""
+    import torch
+    import torch.distributed as dist
+    dev, world = _dist_device(group, device), dist.get_world_size(group)
+    n = torch.tensor([int(ncells)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    return int(sum(int(c.item()) for c in counts[:dist.get_rank(group)]))
+
+
+def _mean_over_ranks(group, value, device=None):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_dist_device(group, device))
+    dist.all_reduce(t, group=group)
+    return float(t.item()) / dist.get_world_size(group)
+
+
+def _global_mean_var_ratio(group, local_sums, sharded_axis, device=None):
     """mean / population variance of the totals along one axis of the sharded matrix.
     Cell totals (sharded axis) are pooled as moments, gene totals are summed over ranks."""
     import torch
     import torch.distributed as dist
-    dev = _dist_device(group)
+    dev = _dist_device(group, device)
     if sharded_axis:
         m = torch.tensor([local_sums.sum(), (local_sums ** 2).sum(), float(local_sums.shape[0])],
                          dtype=torch.float64, device=dev)
@@ -52,11 +75,11 @@ def _global_mean_var_ratio(group, local_sums, sharded_axis):
     return np.mean(tot) / np.var(tot)
 
 
-def _replicate_from_rank0(group, *gammas):
+def _replicate_from_rank0(group, *gammas, device=None):
     """Every rank gets rank 0's copies (the gene side must be identical everywhere)."""
     import torch
     import torch.distributed as dist
-    dev, src, out = _dist_device(group), (dist.get_global_rank(group, 0) if group is not None else 0), []
+    dev, src, out = _dist_device(group, device), (dist.get_global_rank(group, 0) if group is not None else 0), []
     for g in gammas:
         pair = []
         for arr in (g.vi_shape, g.vi_rate):
@@ -67,11 +90,11 @@ def _replicate_from_rank0(group, *gammas):
     return out
 
 
-def _all_gather_rows(group, arr):
+def _all_gather_rows(group, arr, device=None):
     """Rows of every rank's `arr` (same trailing shape, different row counts) in rank order."""
     import torch
     import torch.distributed as dist
-    dev, world = _dist_device(group), dist.get_world_size(group)
+    dev, world = _dist_device(group, device), dist.get_world_size(group)
     n = torch.tensor([arr.shape[0]], dtype=torch.int64, device=dev)
     counts = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(counts, n, group=group)
@@ -84,10 +107,10 @@ def _all_gather_rows(group, arr):
     return np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)]).astype(arr.dtype, copy=False)
 
 
-def _shared_seed(group):
+def _shared_seed(group, rng=np.random):
     """One random-phi seed for all ranks, drawn from rank 0's numpy stream."""
     import torch.distributed as dist
-    box = [int(np.random.randint(0, 2 ** 31 - 1))]
+    box = [int(rng.randint(0, 2 ** 31 - 1))]
     dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     return box[0]
 
@@ -97,12 +120,13 @@ class HPF_Gamma(object):
     (reference: scHPF_.py:27-178)."""
 
     @staticmethod
-    def random_gamma_factory(dims, shape_prior, rate_prior, dtype=np.float64):
+    def random_gamma_factory(dims, shape_prior, rate_prior, dtype=np.float64, rng=np.random):
         """U(0.5 p, 1.5 p) draws, shape first then rate (scHPF_.py:50-70): the
-        order matters for reproducing a seeded reference run."""
+        order matters for reproducing a seeded reference run.  `rng`: numpy's global stream
+        (the reference's) or a RandomState of the caller's (trials on several threads)."""
         lo_hi = lambda p: (0.5 * p, 1.5 * p)
-        vi_shape = np.random.uniform(*lo_hi(shape_prior), dims).astype(dtype)
-        vi_rate = np.random.uniform(*lo_hi(rate_prior), dims).astype(dtype)
+        vi_shape = rng.uniform(*lo_hi(shape_prior), dims).astype(dtype)
+        vi_rate = rng.uniform(*lo_hi(rate_prior), dims).astype(dtype)
         return HPF_Gamma(vi_shape, vi_rate)
 
     def __init__(self, vi_shape, vi_rate):
@@ -166,7 +190,8 @@ class scHPF(BaseEstimator):
     """single-cell Hierarchical Poisson Factorization (Levitin et al., MSB 2019).
 
     Same constructor arguments and defaults as the reference estimator
-    (scHPF_.py:225-246); `device` (CUDA ordinal) is the only addition.
+    (scHPF_.py:225-246); `device` is the only addition: a CUDA ordinal, or a list of ordinals to
+    shard the cells of one fit over several GPUs from this one process (schpf_b200/multi.py).
     """
 
     def __init__(self, nfactors, a=0.3, ap=1, bp=None, c=0.3, cp=1, dp=None,
@@ -195,6 +220,16 @@ class scHPF(BaseEstimator):
         self.theta = theta
         self.beta = beta
         self.loss = []
+
+    # random draws (initialisation, t == 0 Dirichlet, minibatch shuffle): numpy's global stream like
+    # the reference unless a trial runner gave this model a stream of its own (trials.run_trials_pool)
+    @property
+    def _rng(self):
+        return self.__dict__.get("_rng_state") or np.random
+
+    def set_random_state(self, rng):
+        """`rng`: a numpy RandomState (or None for numpy's global stream, the default)."""
+        self.__dict__["_rng_state"] = rng
 
     # a and c accept -2 meaning 1/sqrt(K) (scHPF_.py:284-319)
     def _sqrtk_or(self, val):
@@ -310,19 +345,25 @@ class scHPF(BaseEstimator):
         xi / theta hold the cells of ALL ranks in rank order (collective; every rank gets it).
         Genes, hyperparameters and the loss are already the same everywhere."""
         full = deepcopy(self)
-        full.xi = HPF_Gamma(_all_gather_rows(process_group, self.xi.vi_shape),
-                            _all_gather_rows(process_group, self.xi.vi_rate))
-        full.theta = HPF_Gamma(_all_gather_rows(process_group, self.theta.vi_shape),
-                               _all_gather_rows(process_group, self.theta.vi_rate))
+        gather = lambda arr: _all_gather_rows(process_group, arr, self.device)
+        full.xi = HPF_Gamma(gather(self.xi.vi_shape), gather(self.xi.vi_rate))
+        full.theta = HPF_Gamma(gather(self.theta.vi_shape), gather(self.theta.vi_rate))
         return full
 
     def fit_transform(self, X, y=None, **kwargs):
         return self.fit(X, **kwargs).cell_score()
 
     # ---- the loop ------------------------------------------------------------
-    def _new_engine(self, ncells, ngenes):
+    def _new_engine(self, ncells, ngenes, **options):
         factory = _engine_factory or CaviEngine
-        return factory(ncells, ngenes, self.nfactors, device=self.device)
+        if isinstance(self.device, (list, tuple)):
+            if len(self.device) > 1:
+                # several GPUs from this one process: cells sharded over them (schpf_b200/multi.py)
+                from .multi import LocalShardedEngine
+                return LocalShardedEngine(ncells, ngenes, self.nfactors, devices=self.device,
+                                          engine_factory=factory, **options)
+            return factory(ncells, ngenes, self.nfactors, device=self.device[0], **options)
+        return factory(ncells, ngenes, self.nfactors, device=self.device, **options)
 
     def _fit(self, X, freeze_genes=False, reinit=True, loss_function=None,
              min_iter=None, max_iter=None, epsilon=None, check_freq=None,
@@ -339,14 +380,25 @@ class scHPF(BaseEstimator):
         `process_group` (the only addition): a torch.distributed group whose ranks each pass
         their own contiguous shard of the cells as `X` (all genes).  b', d' come from the whole
         matrix, eta/beta are rank 0's draws on every rank, the loss is the loss over all
-        cells, and the returned xi/theta are this rank's rows."""
+        cells, and the returned xi/theta are this rank's rows.  A custom `loss_function` is
+        evaluated by every rank on ITS cells (that is all `xi` / `theta` hold) and the ranks'
+        values are averaged, so that every rank takes the same stopping decision;
+        `checkstep_function` sees the local cells only."""
         assert loss_smoothing > 0
+        from ._lib import MAX_FACTORS
+        if self.nfactors > MAX_FACTORS:
+            raise ValueError('nfactors={} is above the {} factors the CUDA sweeps are built for'
+                             .format(self.nfactors, MAX_FACTORS))
         nfactors, (ncells, ngenes) = self.nfactors, X.shape
         a, ap, c, cp = self.a, self.ap, self.c, self.cp
         batched = batchsize is not None and 1 < batchsize <= ncells       # scHPF_.py:627
-        if batched and process_group is not None:
-            raise NotImplementedError('minibatches (batchsize) and cell sharding (process_group) '
-                                      'cannot be combined')
+        multi_device = isinstance(self.device, (list, tuple)) and len(self.device) > 1
+        if batched and (process_group is not None or multi_device):
+            raise NotImplementedError('minibatches (batchsize) and cell sharding (process_group, or a list '
+                                      'of devices) cannot be combined')
+        if process_group is not None and multi_device:
+            raise ValueError('give either a process group (one process per GPU) or a list of devices '
+                             '(one process for all of them), not both')
 
         bp, dp, xi, eta, theta, beta = self._setup(X, freeze_genes, reinit, process_group=process_group)
         # capacity shapes are constants of the fit (scHPF_.py:614-618)
@@ -363,12 +415,18 @@ class scHPF(BaseEstimator):
         hyper = (a, ap, bp, c, cp, dp)
         state = dict(theta=(theta.vi_shape, theta.vi_rate), beta=(beta.vi_shape, beta.vi_rate),
                      xi=(xi.vi_shape, xi.vi_rate), eta=(eta.vi_shape, eta.vi_rate))
+        rng = self._rng
         if batched:
             loop = MinibatchLoop(self._new_engine, X, hyper, state, nfactors, batchsize,
-                                 freeze_genes, beta_theta_simultaneous)
+                                 freeze_genes, beta_theta_simultaneous, rng=rng)
         else:
+            engine_options = {}
+            if process_group is not None:
+                # the device's t == 0 draw is keyed by the GLOBAL cell index
+                engine_options["row_offset"] = _global_row_offset(process_group, ncells, self.device)
             loop = FullBatchLoop(self._new_engine, X, hyper, state, nfactors, freeze_genes,
-                                 beta_theta_simultaneous, process_group, _shared_seed)
+                                 beta_theta_simultaneous, process_group, _shared_seed, rng=rng,
+                                 engine_options=engine_options)
         try:
             def host_state():
                 st = loop.host_state()
@@ -394,9 +452,15 @@ class scHPF(BaseEstimator):
                 if loss_function is None:
                     curr = loop.loss()
                 else:
-                    hxi, heta, htheta, hbeta = host_state()
-                    curr = loss_function(a=a, ap=ap, bp=bp, c=c, cp=cp, dp=dp,
-                                         xi=hxi, eta=heta, theta=htheta, beta=hbeta)
+                    if getattr(loss_function, 'accepts_device_loop', False):
+                        # loss.ProjectionLoss: takes beta / eta from the training engine device to device
+                        curr = loss_function.device_call(loop, a=a, ap=ap, bp=bp, c=c, cp=cp, dp=dp)
+                    else:
+                        hxi, heta, htheta, hbeta = host_state()
+                        curr = loss_function(a=a, ap=ap, bp=bp, c=c, cp=cp, dp=dp,
+                                             xi=hxi, eta=heta, theta=htheta, beta=hbeta)
+                    if process_group is not None:
+                        curr = _mean_over_ranks(process_group, curr, self.device)
                 unsmoothed_loss.append(curr)
                 if len(unsmoothed_loss) > loss_smoothing:
                     unsmoothed_loss = unsmoothed_loss[1:]
@@ -444,7 +508,7 @@ class scHPF(BaseEstimator):
         a, ap, c, cp = self.a, self.ap, self.c, self.cp
         xi, eta, theta, beta = self.xi, self.eta, self.theta, self.beta
         bp, dp = self._get_empirical_hypers(X, freeze_genes, clip, process_group=process_group)
-        make = HPF_Gamma.random_gamma_factory
+        make = lambda *args, **kw: HPF_Gamma.random_gamma_factory(*args, rng=self._rng, **kw)
         if reinit or xi is None:
             xi = make((ncells,), ap, bp, dtype=self.dtype)
         if reinit or theta is None:
@@ -460,7 +524,7 @@ class scHPF(BaseEstimator):
             if reinit or beta is None:
                 beta = make((ngenes, nfactors), c, dp, dtype=self.dtype)
             if process_group is not None:
-                eta, beta = _replicate_from_rank0(process_group, eta, beta)
+                eta, beta = _replicate_from_rank0(process_group, eta, beta, device=self.device)
         return (bp, dp, xi, eta, theta, beta)
 
     def _get_empirical_hypers(self, X, freeze_genes=False, clip=True, process_group=None):
@@ -473,7 +537,7 @@ class scHPF(BaseEstimator):
             axis_sum = X.sum(axis=axis)
             if process_group is not None:
                 return _global_mean_var_ratio(process_group, np.asarray(axis_sum, dtype=np.float64).ravel(),
-                                              sharded_axis=(axis == 1))
+                                              sharded_axis=(axis == 1), device=self.device)
             return np.mean(axis_sum) / np.var(axis_sum)
         if bp is None:
             bp = self.ap * mean_var_ratio(1)

@@ -10,7 +10,8 @@ differ from the reference on purpose:
   re-uploading it at every check; the value is the same number;
 * `run_trials_pool` spreads trials over GPUs (`devices`, one worker thread per
   device -- the C ABI releases the GIL) instead of over joblib CPU processes;
-  `njobs` / `max_threads` are accepted and ignored.
+  `njobs` / `max_threads` are accepted and ignored.  Each trial is the reference's
+  (a full `fit` with `reinit=True`); it draws from a RandomState of its own.
 """
 from functools import partial
 import threading
@@ -69,6 +70,8 @@ def run_trials(X, nfactors, ntrials=5, min_iter=30, max_iter=1000, check_freq=10
                       dtype=dtype, **model_kwargs)
         model.fit(X, loss_function=fit_loss, checkstep_function=checkstep, batchsize=batchsize,
                   loss_smoothing=loss_smoothing, beta_theta_simultaneous=beta_theta_simultaneous)
+        if hasattr(fit_loss, 'close'):
+            fit_loss.close()                    # the validation cells' engine
         if reproject:
             print('Reprojecting data...')
             kw = dict(reproject_kwargs, replace=True, reinit=False)
@@ -103,9 +106,15 @@ def run_trials_pool(X, nfactors, ntrials=5, njobs=0, max_threads=None, min_iter=
     """Trials for one or several K, spread over GPUs (scHPF_.py:1151-1332).  Returns the list
     of best models, one per K (plus the rejected ones per K when `return_all`).
 
-    Initial draws come from the numpy global RNG on the calling thread, trial by trial in
-    (K, trial) order, BEFORE any work is dispatched, so a seeded call is reproducible whatever
-    the number of devices."""
+    Every trial is what the reference's pool runs (scHPF_.py:1286-1297): a full `fit` with
+    `reinit=True`, i.e. random initialisation AND the t == 0 random-phi iteration.  Trials run on
+    one worker thread per device, so each gets a random stream of its own: one integer seed per
+    trial is drawn from numpy's global stream on the calling thread, in (K, trial) order, before
+    any work is dispatched, and the trial's draws (initialisation, t == 0 Dirichlet, minibatch
+    shuffle, validation-cell projection) all come from `RandomState(seed)`.  A seeded call is
+    therefore reproducible whatever the number of devices, and trial i equals
+    `m = scHPF(K); m.set_random_state(RandomState(seed_i)); m.fit(X)`.  An exception in a worker
+    is re-raised here after all workers have stopped."""
     _gene_count_warning(X.shape[1])
     ks = [nfactors] if isinstance(nfactors, (int, np.integer)) else list(nfactors)
     if devices is None:
@@ -118,26 +127,40 @@ def run_trials_pool(X, nfactors, ntrials=5, njobs=0, max_threads=None, min_iter=
             model = scHPF(nfactors=K, min_iter=min_iter, max_iter=max_iter, check_freq=check_freq,
                           epsilon=epsilon, better_than_n_ago=better_than_n_ago, verbose=False,
                           dtype=dtype, **model_kwargs)
-            model._initialize(X)                       # RNG consumed here, in order
+            model.set_random_state(np.random.RandomState(int(np.random.randint(0, 2 ** 31 - 1))))
             jobs.append(model)
+    errors = []
 
     def work(dev):
-        for i in range(dev, len(jobs), len(devices)):
-            m = jobs[i]
-            m.device = devices[dev]
-            fit_loss, _ = _loss_setup(X, m.nfactors, vcells, vX, loss_function, check_freq)
-            # reinit=False: the draws above are the initialisation (no t=0 Dirichlet step)
-            m.fit(X, loss_function=fit_loss, reinit=False, batchsize=batchsize,
-                  loss_smoothing=loss_smoothing, beta_theta_simultaneous=beta_theta_simultaneous)
-            if reproject:
-                kw = dict(reproject_kwargs, replace=True, reinit=False)
-                m.loss.append(m.project(X, **kw))
+        try:
+            for i in range(dev, len(jobs), len(devices)):
+                if errors:
+                    return
+                m = jobs[i]
+                m.device = devices[dev]
+                fit_loss, _ = _loss_setup(X, m.nfactors, vcells, vX, loss_function, check_freq)
+                if hasattr(fit_loss, 'pmodel'):            # validation-cell projections draw from the trial's stream
+                    fit_loss.pmodel.set_random_state(m._rng)
+                    fit_loss.pmodel.device = m.device
+                m.fit(X, loss_function=fit_loss, batchsize=batchsize, loss_smoothing=loss_smoothing,
+                      beta_theta_simultaneous=beta_theta_simultaneous)
+                if reproject:
+                    kw = dict(reproject_kwargs, replace=True, reinit=False)
+                    m.loss.append(m.project(X, **kw))
+                if hasattr(fit_loss, 'close'):
+                    fit_loss.close()
+                m.set_random_state(None)                   # the returned model pickles like any other
+        except BaseException as exc:                       # noqa: B902 -- re-raised on the calling thread
+            errors.append((dev, exc))
 
     threads = [threading.Thread(target=work, args=(d,)) for d in range(len(devices))]
     for th in threads:
         th.start()
     for th in threads:
         th.join()
+    if errors:
+        dev, exc = errors[0]
+        raise RuntimeError('run_trials_pool: the worker of device {} failed: {!r}'.format(devices[dev], exc)) from exc
 
     best, rejected = [], []
     for i, K in enumerate(ks):

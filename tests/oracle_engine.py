@@ -13,6 +13,8 @@ from oracle import hpf_numpy as onp
 class OracleEngine(object):
     def __init__(self, ncells, ngenes, nfactors, device=0, stream=None, **options):
         self.ncells, self.ngenes, self.nfactors = int(ncells), int(ngenes), int(nfactors)
+        self.device = int(device)
+        self.row_offset = int(options.get("row_offset", 0))
         self.nnz = 0
         self.st = None
         self._exch = None
@@ -86,11 +88,17 @@ class OracleEngine(object):
         self.set_state(beta=(o.beta_shp, o.beta_rte), eta=(o.eta_shp, o.eta_rte))
 
     # ---- split phase (cell sharding) ----------------------------------------
-    def step_begin(self, freeze_genes=False, simultaneous=False, random_phi_seed=None):
+    def step_begin(self, freeze_genes=False, simultaneous=False, random_phi_seed=None, xphi=None):
         s, K = self.st, self.nfactors
-        assert random_phi_seed is None
-        self._xphi = onp.compute_Xphi_data(self.data, self.row, self.col, s.theta_shp, s.theta_rte,
-                                           s.beta_shp, s.beta_rte)
+        if xphi is not None:
+            self._xphi = np.asarray(xphi, dtype=np.float64)
+        elif random_phi_seed is not None:
+            # t == 0: y * Dirichlet(1_K), a stream of this shard's own (keyed like the device's by the shard offset)
+            rng = np.random.default_rng([int(random_phi_seed), self.row_offset])
+            self._xphi = self.data[:, None] * rng.dirichlet(np.ones(K), self.nnz)
+        else:
+            self._xphi = onp.compute_Xphi_data(self.data, self.row, self.col, s.theta_shp, s.theta_rte,
+                                               s.beta_shp, s.beta_rte)
         if not freeze_genes:
             buf = self.exchange_tensor().numpy()
             part = onp.compute_loading_shape_update(self._xphi, self.col, self.ngenes, 0.0)

@@ -143,6 +143,12 @@ def test_estimator_reinit_and_project_match_seeded_reference(g_reinit, g_cavi, g
     assert max_rel(proj.xi.vi_rate, p["xi_rte"]) < TOL
     assert_allclose(proj.loss, p["loss"], rtol=1e-11)
     assert_allclose(proj.cell_score(), p["cell_score"], rtol=1e-9)
+    # transform(): the sklearn-convention alias = cell scores of the projected cells (same seed, same draw)
+    np.random.seed(int(p["seed"]))
+    scores = trained.transform(_X(p), min_iter=10, max_iter=10, check_freq=2)
+    assert scores.shape == p["cell_score"].shape
+    assert_allclose(scores, p["cell_score"], rtol=1e-9)
+    assert trained.theta.vi_shape.shape[0] == int(c["shape"][0])       # the trained model is untouched
 
 
 def test_float32_models_keep_their_dtype_and_track_the_reference(g_fp32):

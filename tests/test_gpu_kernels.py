@@ -57,6 +57,13 @@ def test_compute_Xphi_data(g_kernels, dtype):
     assert_allclose(got, g["Xphi"], rtol=1e-12 if dtype == np.float64 else 1e-5, atol=0)
     if dtype == np.float64:
         assert_allclose(got.sum(1), g["data"], rtol=1e-14)
+    # the reference's single-process twin (hpf_numba.py:117-125) is the same device kernel here
+    from scipy.sparse import coo_matrix
+    from schpf_b200 import HPF_Gamma
+    data, row, col = _coo(g)
+    X = coo_matrix((data, (row, col)), shape=tuple(int(v) for v in g["shape"]))
+    twin = hpf_cuda.compute_Xphi_data_numpy(X, HPF_Gamma(args[0], args[1]), HPF_Gamma(args[2], args[3]))
+    assert twin.dtype == dtype and np.array_equal(twin, got)
 
 
 def test_shape_updates(g_kernels):

@@ -18,12 +18,9 @@ from oracle import hpf_numpy as onp
 
 pytestmark = pytest.mark.gpu
 
-# schpf_copy_cell_state and MinibatchLoop(device_state=True) were written after the last GPU
-# minutes of round 1 were spent: their host logic is covered on CPU (tests/test_host_cpu.py),
-# the device copies run only on request until they have been seen to pass on hardware.
-unvalidated = pytest.mark.skipif(not os.environ.get("SCHPF_TEST_UNVALIDATED"),
-                                 reason="not yet run on hardware; set SCHPF_TEST_UNVALIDATED=1")
-DEVICE_STATE = [False, pytest.param(True, marks=unvalidated)]
+# device_state=True (theta / xi of all cells resident in HBM, batches moved with
+# schpf_copy_cell_state) is the default since it passed on hardware (round 2, gpurun_out/r2a_tests_gpu.log)
+DEVICE_STATE = [False, True]
 
 NAMES = ("theta", "beta", "xi", "eta")
 TOL = 1e-9
@@ -125,7 +122,6 @@ def test_copy_gene_state_between_engines():
             wrong.copy_gene_state_from(a)               # ngenes differ
 
 
-@unvalidated
 def test_copy_cell_state_between_engines():
     row, col, data, st = _problem(80, 64, 5, 1500, 1)
     row2, col2, data2, st2 = _problem(33, 64, 5, 700, 2)

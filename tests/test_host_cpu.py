@@ -426,3 +426,75 @@ def test_run_trials_pool_over_devices(oracle_backend, g_reinit):
     np.random.seed(5)
     again = run_trials_pool(X, [2, 3], ntrials=2, min_iter=3, max_iter=3, check_freq=1, devices=[0])
     assert all(np.array_equal(a.beta.vi_shape, b.beta.vi_shape) for a, b in zip(again, best))
+
+
+def test_run_trials_pool_trials_are_full_fits_with_their_own_stream(oracle_backend, g_reinit):
+    """a pool trial is what the reference's pool runs -- a fit with reinit=True, i.e.
+    random initialisation AND the t == 0 random-phi iteration -- from a RandomState of its own,
+    seeded from numpy's global stream on the calling thread in (K, trial) order."""
+    from schpf_b200 import run_trials_pool, scHPF
+    X = _X(g_reinit)
+    np.random.seed(11)
+    best, rejected = run_trials_pool(X, 3, ntrials=3, min_iter=4, max_iter=4, check_freq=2, return_all=True,
+                                     devices=[0, 0])
+    models = [best[0]] + rejected[0]
+    np.random.seed(11)
+    seeds = [int(np.random.randint(0, 2 ** 31 - 1)) for _ in range(3)]
+    direct = []
+    for s in seeds:
+        m = scHPF(3, min_iter=4, max_iter=4, check_freq=2, verbose=False)
+        m.set_random_state(np.random.RandomState(s))
+        m.fit(X)                                     # reinit=True by default
+        direct.append(m)
+    by_loss = sorted(direct, key=lambda m: m.loss[-1])
+    for a, b in zip(models, by_loss):
+        assert np.array_equal(a.beta.vi_shape, b.beta.vi_shape) and a.loss == b.loss
+    # and it is NOT the reinit=False trajectory from the same initial draws (the old pool)
+    m0 = scHPF(3, min_iter=4, max_iter=4, check_freq=2, verbose=False)
+    m0.set_random_state(np.random.RandomState(seeds[0]))
+    m0._initialize(X)
+    m0.fit(X, reinit=False)
+    assert not np.allclose(m0.beta.vi_shape, direct[0].beta.vi_shape)
+
+
+def test_run_trials_pool_reraises_worker_errors(oracle_backend, g_reinit, monkeypatch):
+    from schpf_b200 import run_trials_pool
+    from schpf_b200 import scHPF_ as shell
+    X = _X(g_reinit)
+
+    class Boom(shell._engine_factory):
+        def set_coo(self, *a):
+            raise MemoryError("device out of memory (simulated)")
+    monkeypatch.setattr(shell, "_engine_factory", Boom)
+    with pytest.raises(RuntimeError, match="worker of device 0 failed.*out of memory"):
+        run_trials_pool(X, 3, ntrials=2, min_iter=2, max_iter=2, check_freq=1, devices=[0])
+
+
+def test_more_factors_than_the_kernels_support_is_a_python_error():
+    from schpf_b200 import scHPF
+    X = coo_matrix((np.ones(4, dtype=np.int32), (np.arange(4), np.arange(4))), shape=(4, 4))
+    with pytest.raises(ValueError, match="above the 64 factors"):
+        scHPF(65, verbose=False).fit(X, max_iter=1, min_iter=1)
+
+
+def test_fit_on_a_list_of_devices_shards_the_cells_in_one_process(oracle_backend, g_cavi):
+    """scHPF(K, device=[0, 1, 2]).fit(X): one process, cells cut by nnz over the devices, the
+    exchange buffers summed every iteration (here through the oracle-backed engines): the
+    reference's unsharded golden run, incl. the t == 0 branch being well defined."""
+    g, X = g_cavi, _X(g_cavi)
+    gam = lambda n: HPF_Gamma(g["init_" + n + "_shp"].copy(), g["init_" + n + "_rte"].copy())
+    m = scHPF(5, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]), device=[0, 1, 2],
+              xi=gam("xi"), theta=gam("theta"), eta=gam("eta"), beta=gam("beta"))
+    m.fit(X, reinit=False, min_iter=10, max_iter=10, check_freq=3)
+    for n in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(m, n).vi_shape, g["it10_" + n + "_shp"]) < 1e-11, n
+        assert max_rel(getattr(m, n).vi_rate, g["it10_" + n + "_rte"]) < 1e-11, n
+    assert_allclose(m.loss, g["it10_loss"], rtol=1e-12)
+    # projection (frozen genes: no exchange) and a reinit=True fit run too
+    proj = m.project(X, min_iter=2, max_iter=2, check_freq=1, verbose=False)
+    assert proj.theta.vi_shape.shape == m.theta.vi_shape.shape and np.isfinite(proj.loss[-1])
+    np.random.seed(0)
+    m2 = scHPF(5, verbose=False, device=[0, 1]).fit(X, min_iter=2, max_iter=2, check_freq=1)
+    assert abs((m2.beta.vi_shape - m2.c).sum() / X.data.sum() - 1) < 1e-9
+    with pytest.raises(NotImplementedError):
+        scHPF(5, verbose=False, device=[0, 1]).fit(X, batchsize=100, max_iter=1, min_iter=1)

@@ -144,3 +144,57 @@ def test_estimator_fit_with_process_group(tmp_path):
     for k in range(world):
         assert np.array_equal(r[k]["full_theta_shp"], np.concatenate([r[0]["theta_shp"], r[1]["theta_shp"]]))
         assert np.array_equal(r[k]["full_xi_rte"], np.concatenate([r[0]["xi_rte"], r[1]["xi_rte"]]))
+
+
+def _custom_loss_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from scipy.sparse import coo_matrix
+    from schpf_b200 import scHPF
+    from schpf_b200 import scHPF_ as shell
+    from schpf_b200 import loss as ls
+    from schpf_b200.engine import shard_coo_rows
+    from oracle_engine import OracleEngine
+    from oracle import hpf_numpy as onp
+    shell._engine_factory = OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = dict(np.load(os.path.join(GOLDEN, "cavi_cfg1.npz")))
+    C, G = (int(v) for v in g["shape"])
+    X, lo, hi = shard_coo_rows(coo_matrix((g["data"], (g["row"], g["col"])), shape=(C, G)), rank, world)
+    offsets = []
+
+    class Spy(OracleEngine):
+        def __init__(self, *a, **kw):
+            offsets.append(kw.get("row_offset"))
+            OracleEngine.__init__(self, *a, **kw)
+    shell._engine_factory = Spy
+
+    def local_loss(*, theta, beta, **kw):        # each rank sees ITS cells only: values differ between ranks
+        return float(np.mean(-onp.compute_pois_llh(X.data, X.row, X.col, theta.vi_shape, theta.vi_rate,
+                                                   beta.vi_shape, beta.vi_rate))) * (1.0 + 0.5 * rank)
+    np.random.seed(3 + rank)                     # different streams: the shared seed must come from rank 0
+    m = scHPF(5, verbose=False, epsilon=5.0)     # (the estimator's epsilon is the one _fit reads, as in the reference)
+    # reinit=True: random initialisation and the t == 0 random-phi step under a process group; a
+    # rank-local custom loss with loose stopping rules: every rank must stop at the same iteration
+    m.fit(X, min_iter=2, max_iter=40, check_freq=2, loss_function=local_loss, process_group=dist.group.WORLD)
+    np.savez(os.path.join(out_dir, "cl%d.npz" % rank), loss=np.array(m.loss), beta_shp=m.beta.vi_shape,
+             offset=np.array(offsets[0]), lo=lo)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_custom_loss_and_reinit_under_a_process_group(tmp_path):
+    """a rank-local custom loss must not let ranks stop at different iterations (the
+    values are averaged over ranks before the stopping rules), the engines get the global cell
+    offset of their shard, and reinit=True (random-phi first iteration) works when sharded."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_custom_loss_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [dict(np.load(str(tmp_path / ("cl%d.npz" % k)))) for k in range(world)]
+    assert np.array_equal(r[0]["loss"], r[1]["loss"]) and len(r[0]["loss"]) >= 2
+    assert len(r[0]["loss"]) < 20                                  # stopped early, together
+    assert np.array_equal(r[0]["beta_shp"], r[1]["beta_shp"])      # replicas still identical
+    assert int(r[0]["offset"]) == 0 and int(r[1]["offset"]) == int(r[1]["lo"]) > 0
