@@ -133,7 +133,22 @@ __device__ __forceinline__ double pair_sum_mma(double p, double sel)
 struct TabGeom {
     int KA, KB;
     int64_t offB;
+    // fp32 sweep (sweep_f32.cu): the table is ALSO written as floats, rows of `kf` floats, and the fp64
+    // copy then holds the float-rounded value (the finalisation multiplies by what the sweep read)
+    float *f32 = nullptr;
+    int kf = 0;
 };
+// store one table element in every copy the geometry asks for; returns the value the fp64 copy holds
+__device__ __forceinline__ double tab_store(const TabGeom &g, double *tab, int64_t i, int k, double v)
+{
+    if (g.f32) {
+        const float f = (float)v;
+        g.f32[i * g.kf + k] = f;
+        v = (double)f;
+    }
+    tab[k < g.KA ? i * g.KA + k : g.offB + i * g.KB + (k - g.KA)] = v;
+    return v;
+}
 __host__ __device__ __forceinline__ int64_t tab_index(const TabGeom &g, int64_t i, int k)
 {
     return k < g.KA ? i * g.KA + k : g.offB + i * g.KB + (k - g.KA);
@@ -317,6 +332,12 @@ int lanes_default_warps(int K);
 int launch_lane_sweep(int mode, int K, const SideLayout &L, const SweepArgs &args, cudaStream_t stream);
 inline size_t lane_sweep_smem_bytes(int KP, int panel_rows) { return (size_t)panel_rows * KP * 8 + 16 + 16 * 8; }
 int lanes_max_panel_rows(int K);
+// fp32 one-lane-per-owner kernels (sweep_f32.cu): tables of 32 (K <= 32) or 64 floats per row
+int f32_row_floats(int K);
+int f32_default_warps(int K);
+int f32_max_panel_rows(int K);
+size_t f32_sweep_smem_bytes(int K, int panel_rows, int warps);
+int launch_f32_sweep(int mode, int K, const SideLayout &L, const SweepArgs &args, cudaStream_t stream);
 size_t sweep_smem_bytes(int K, int panel_rows);
 int max_panel_rows(int K, int ctas_per_sm);
 

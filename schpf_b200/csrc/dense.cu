@@ -109,7 +109,7 @@ finalize_kernel(int64_t n, int K, TabGeom tg, double prior_shape, double prior_r
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const int k = lane + 32 * t;
-            if (k < K) Etab[tab_index(tg, i, k)] = exp(el[t] - m);
+            if (k < K) tab_store(tg, Etab, i, k, exp(el[t] - m));
         }
     }
     if (colsum_out) {
@@ -137,7 +137,7 @@ __global__ void ex_table_kernel(int64_t n, int K, TabGeom tg, const double *__re
     if (idx >= n * K) return;
     const int64_t i = idx / K;
     const int k = (int)(idx - i * K);
-    X[tab_index(tg, i, k)] = shp[idx] / rte[idx];
+    tab_store(tg, X, i, k, shp[idx] / rte[idx]);
 }
 
 // out[i,k] = E[i,k] * acc[i,k] + direct[i,k] : this shard's part of

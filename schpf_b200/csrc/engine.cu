@@ -127,8 +127,14 @@ struct schpf_engine {
     // sweep family and table geometry (common.cuh TabGeom): lanes = one-lane-per-owner kernels
     bool lanes = false;
     int KA = 0, KB = 0;
-    TabGeom geom_t() const { return TabGeom{KA, KB, C_pad * KA}; }
-    TabGeom geom_b() const { return TabGeom{KA, KB, G_pad * KA}; }
+    // fp32 sweep (option "precision" = 32, sweep_f32.cu): float copies of the four streamed tables
+    bool f32 = false;
+    int KF = 0;                                      // floats per row of the fp32 tables
+    float *Et32 = nullptr, *Eb32 = nullptr, *Xt32 = nullptr, *Xb32 = nullptr;
+    TabGeom geom_t() const { return TabGeom{KA, KB, C_pad * KA, Et32, KF}; }
+    TabGeom geom_b() const { return TabGeom{KA, KB, G_pad * KA, Eb32, KF}; }
+    TabGeom geom_xt() const { return TabGeom{KA, KB, C_pad * KA, Xt32, KF}; }
+    TabGeom geom_xb() const { return TabGeom{KA, KB, G_pad * KA, Xb32, KF}; }
 
     // options
     int opt_panel_rows = 0;     // 0 = largest that fits
@@ -138,6 +144,7 @@ struct schpf_engine {
     int opt_timing = 0;
     int opt_packed_entries = 0; // 1 = 4-byte stream entries when every count is < 2^19
     int opt_lanes = 1;          // 0 = lane-pair kernels for every K (sweep.cu)
+    int opt_precision = 64;     // 32 = fp32 sweep for float32 models (sweep_f32.cu); state and updates stay fp64
     int opt_rank_per_range = -1; // -1 = automatic (on for streams without a bank schedule); 0 / 1
     int opt_free_schedule = -1;  // K 17..20 (plane B): 1 = no bank schedule (rotated class order instead), 0 = 4x4 colouring
     int64_t row_offset = 0;     // global index of local cell 0 (random-phi stream)
@@ -250,7 +257,8 @@ int timed_sweep(schpf_engine *h, int mode, const SideLayout &L, const SweepArgs 
         ++h->ev_used;
         CUDA_TRY(cudaEventRecord(e0, h->stream));
     }
-    if (L.opw == 32) RC_TRY(launch_lane_sweep(mode, h->K, L, args, h->stream));
+    if (h->f32) RC_TRY(launch_f32_sweep(mode, h->K, L, args, h->stream));
+    else if (L.opw == 32) RC_TRY(launch_lane_sweep(mode, h->K, L, args, h->stream));
     else RC_TRY(launch_sweep(mode, h->K, L, args, h->stream));
     if (h->opt_timing) CUDA_TRY(cudaEventRecord(e1, h->stream));
     h->n_sweeps += 1;
@@ -341,8 +349,8 @@ int cells_sweep(schpf_engine *h)
 {
     // theta side: cells own, gene panels stream through shared memory
     SweepArgs A = side_args(h, h->cells);
-    A.own_tab = h->Et;
-    A.oth_tab = h->Eb;
+    A.own_tab = h->f32 ? reinterpret_cast<const double *>(h->Et32) : h->Et;
+    A.oth_tab = h->f32 ? reinterpret_cast<const double *>(h->Eb32) : h->Eb;
     A.acc = h->acc_t;
     A.own_elog = h->elog_t;
     A.oth_elog = h->elog_b;
@@ -356,8 +364,8 @@ int genes_sweep(schpf_engine *h)
 {
     // beta side: genes own, cell panels stream
     SweepArgs B = side_args(h, h->genes);
-    B.own_tab = h->Eb;
-    B.oth_tab = h->Et;
+    B.own_tab = h->f32 ? reinterpret_cast<const double *>(h->Eb32) : h->Eb;
+    B.oth_tab = h->f32 ? reinterpret_cast<const double *>(h->Et32) : h->Et;
     B.acc = h->acc_b;
     B.own_elog = h->elog_b;
     B.oth_elog = h->elog_t;
@@ -499,7 +507,9 @@ int finish_coo(schpf_engine *h)
         return SCHPF_ERR_ARG;
     }
     // sweep family for this K: one lane per owner where it is instantiated, lane pairs otherwise
-    h->lanes = h->opt_lanes && h->opt_variant == 0 && lanes_supported(h->K);
+    h->f32 = h->opt_precision == 32 && h->opt_variant == 0;
+    h->KF = h->f32 ? f32_row_floats(h->K) : 0;
+    h->lanes = !h->f32 && h->opt_lanes && h->opt_variant == 0 && lanes_supported(h->K);
     if (h->lanes) {
         const int kp = lanes_kp_of(h->K);
         h->KB = kp == 20 ? 4 : 0;
@@ -510,8 +520,8 @@ int finish_coo(schpf_engine *h)
     }
     const int TW = h->KA + h->KB;     // doubles per table row
     const int ctas = sweep_ctas_per_sm(h->K);
-    const int Pmax = h->lanes ? lanes_max_panel_rows(h->K) : max_panel_rows(h->K, 1);
-    int Po = h->opt_panel_rows > 0 ? h->opt_panel_rows : h->lanes ? Pmax : max_panel_rows(h->K, ctas);
+    const int Pmax = h->f32 ? f32_max_panel_rows(h->K) : h->lanes ? lanes_max_panel_rows(h->K) : max_panel_rows(h->K, 1);
+    int Po = h->opt_panel_rows > 0 ? h->opt_panel_rows : (h->lanes || h->f32) ? Pmax : max_panel_rows(h->K, ctas);
     if (Po > Pmax) Po = Pmax;
     Po &= ~3;
     if (Po < 4) Po = 4;
@@ -533,6 +543,21 @@ int finish_coo(schpf_engine *h)
     }
     h->C_pad = C_pad;
     h->G_pad = G_pad;
+    dev_free(h->Et32);
+    dev_free(h->Eb32);
+    dev_free(h->Xt32);
+    dev_free(h->Xb32);
+    if (h->f32) {
+        const size_t nt = (size_t)C_pad * h->KF, nb = (size_t)G_pad * h->KF;
+        RC_TRY(dev_alloc(&h->Et32, (int64_t)nt));
+        RC_TRY(dev_alloc(&h->Xt32, (int64_t)nt));
+        RC_TRY(dev_alloc(&h->Eb32, (int64_t)nb));
+        RC_TRY(dev_alloc(&h->Xb32, (int64_t)nb));
+        CUDA_TRY(cudaMemsetAsync(h->Et32, 0, sizeof(float) * nt, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->Xt32, 0, sizeof(float) * nt, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->Eb32, 0, sizeof(float) * nb, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->Xb32, 0, sizeof(float) * nb, h->stream));
+    }
     // pad rows / pad columns of the streamed tables stay zero for the lifetime of the layout
     CUDA_TRY(cudaMemsetAsync(h->Et, 0, sizeof(double) * (size_t)C_pad * TW, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->Eb, 0, sizeof(double) * (size_t)G_pad * TW, h->stream));
@@ -540,7 +565,7 @@ int finish_coo(schpf_engine *h)
     CUDA_TRY(cudaMemsetAsync(h->Xb, 0, sizeof(double) * (size_t)G_pad * TW, h->stream));
     h->tables_t_valid = h->tables_b_valid = false;
 
-    int warps = h->lanes ? lanes_default_warps(h->K) : sweep_default_warps(h->K);
+    int warps = h->f32 ? f32_default_warps(h->K) : h->lanes ? lanes_default_warps(h->K) : sweep_default_warps(h->K);
     if (h->opt_warps > 0 && h->opt_warps < warps) warps = h->opt_warps;
     int opw = GROUPS_PER_WARP, lflags = 0;
     if (h->lanes) {
@@ -556,13 +581,18 @@ int finish_coo(schpf_engine *h)
         // (measured at K=20 with the plane-B schedule too: 19 % -> 15 % pads, 3.25 -> 3.15 ms per pair)
         const bool rank = h->opt_rank_per_range < 0 ? true : h->opt_rank_per_range != 0;
         if (rank) lflags |= LAYOUT_RANK_PER_RANGE | LAYOUT_SINGLE_PANEL_RANGES;
+    } else if (h->f32) {
+        // every fp32 row starts at bank group 0: no bank schedule; counts stay plain integers
+        opw = 32;
+        lflags |= LAYOUT_FREE;
+        if (h->opt_rank_per_range != 0) lflags |= LAYOUT_RANK_PER_RANGE | LAYOUT_SINGLE_PANEL_RANGES;
     }
     trace_mark(h->stream, "validate + tables");
     // 4-byte entries are possible when every count fits 19 bits (flag bit 8 = some count >= 2^19).
     // Measured on cfg-3 they are SLOWER than 8-byte entries (3.61 vs 3.43 ms per sweep pair: the
     // sweep is not HBM-bound and the decode costs issue slots), so they are opt-in: they halve
     // the resident layout (1.8 GB instead of 3.6 GB at 1.9e8 nnz) when memory matters.
-    const bool packed = !h->lanes && h->opt_packed_entries && !(flag & 8) && Po <= (1 << PACKED_ROW_BITS);
+    const bool packed = !h->lanes && !h->f32 && h->opt_packed_entries && !(flag & 8) && Po <= (1 << PACKED_ROW_BITS);
     RC_TRY(build_side_layout(h->cells, h->stream, h->nnz, h->row, h->col, h->data, h->C, h->G, Po, warps,
                              h->opt_target_ctas, packed, opw, lflags));
     trace_mark(h->stream, "layout cells total");
@@ -689,6 +719,7 @@ int schpf_destroy(schpf_engine_t *h)
     dev_free(h->theta_shp); dev_free(h->theta_rte); dev_free(h->beta_shp); dev_free(h->beta_rte);
     dev_free(h->xi_shp); dev_free(h->xi_rte); dev_free(h->eta_shp); dev_free(h->eta_rte);
     dev_free(h->Et); dev_free(h->Eb); dev_free(h->Xt); dev_free(h->Xb); dev_free(h->elog_t); dev_free(h->elog_b);
+    dev_free(h->Et32); dev_free(h->Eb32); dev_free(h->Xt32); dev_free(h->Xb32);
     dev_free(h->accum); dev_free(h->exch); dev_free(h->colsum_b); dev_free(h->colsum_t_next);
     dev_free(h->partials); dev_free(h->scalars); dev_free(h->slow_hits); dev_free(h->flag);
     dev_free(h->overflow);
@@ -716,6 +747,17 @@ int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value)
     else if (!strcmp(key, "row_offset")) h->row_offset = value;
     else if (!strcmp(key, "overlap_exchange")) h->opt_overlap_exchange = (int)value;
     else if (!strcmp(key, "lanes")) h->opt_lanes = (int)value;
+    else if (!strcmp(key, "precision")) {
+        if (value != 32 && value != 64) {
+            set_error("precision must be 32 or 64");
+            return SCHPF_ERR_ARG;
+        }
+        if (h->have_coo && (int)value != h->opt_precision) {
+            set_error("precision must be set before the matrix (it selects the layout)");
+            return SCHPF_ERR_STATE;
+        }
+        h->opt_precision = (int)value;
+    }
     else if (!strcmp(key, "rank_per_range")) h->opt_rank_per_range = (int)value;
     else if (!strcmp(key, "free_schedule")) h->opt_free_schedule = (int)value;
     else {
@@ -1014,11 +1056,11 @@ int schpf_loss_parts(schpf_engine_t *h, double *sum_llh, int64_t *count)
     RC_TRY(require_ready(h));
     const int K = h->K;
     // e_x tables in the sweep layout (hpf_numba.py:33-41)
-    RC_TRY(launch_ex_table(h->stream, h->C, K, h->geom_t(), h->theta_shp, h->theta_rte, h->Xt));
-    RC_TRY(launch_ex_table(h->stream, h->G, K, h->geom_b(), h->beta_shp, h->beta_rte, h->Xb));
+    RC_TRY(launch_ex_table(h->stream, h->C, K, h->geom_xt(), h->theta_shp, h->theta_rte, h->Xt));
+    RC_TRY(launch_ex_table(h->stream, h->G, K, h->geom_xb(), h->beta_shp, h->beta_rte, h->Xb));
     SweepArgs A = side_args(h, h->cells);
-    A.own_tab = h->Xt;
-    A.oth_tab = h->Xb;
+    A.own_tab = h->f32 ? reinterpret_cast<const double *>(h->Xt32) : h->Xt;
+    A.oth_tab = h->f32 ? reinterpret_cast<const double *>(h->Xb32) : h->Xb;
     A.partial = h->partials;
     RC_TRY(timed_sweep(h, SWEEP_LLH, h->cells, A));
     RC_TRY(launch_sum_partials(h->stream, h->partials, h->cells.nblocks * h->cells.nranges, h->scalars));
@@ -1144,7 +1186,11 @@ int schpf_comm_attach(schpf_engine_t *h, void *comm)
     RC_TRY(check_handle(h));
     if (comm) RC_TRY(load_nccl());
     if (comm && !h->xstream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking));
+        // highest priority: the all-reduce's few CTAs are placed as soon as a sweep CTA retires (the
+        // sweep fills every SM; at default priority the collective waited for the sweep's tail)
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->xstream, cudaStreamNonBlocking, prio_hi));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_folded, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_reduced, cudaEventDisableTiming));
     }
@@ -1175,6 +1221,7 @@ int schpf_counter(schpf_engine_t *h, const char *what, double *value)
     else if (!strcmp(what, "layout_bytes")) *value = (double)(h->cells.bytes + h->genes.bytes);
     else if (!strcmp(what, "panel_rows")) *value = (double)h->cells.panel_rows;
     else if (!strcmp(what, "lanes")) *value = h->cells.opw == 32 ? 1.0 : 0.0;
+    else if (!strcmp(what, "precision")) *value = h->f32 ? 32.0 : 64.0;
     else if (!strcmp(what, "warps_per_cta")) *value = (double)h->cells.warps;
     else if (!strcmp(what, "packed_entries")) *value = h->cells.packed ? 1.0 : 0.0;
     else if (!strcmp(what, "grid_cells")) *value = (double)h->cells.nblocks * h->cells.nranges;

@@ -24,6 +24,8 @@ from .engine import CaviEngine
 
 # tests substitute an oracle-backed engine here; product code never does
 _engine_factory = None
+# float32 models use the fp32 sweep kernels (False: fp64 arithmetic on fp32-rounded inputs, as in round 1)
+FP32_SWEEP = True
 
 
 # ---- helpers for cell-sharded fits (torch.distributed; any backend) ----------------
@@ -356,6 +358,10 @@ class scHPF(BaseEstimator):
     # ---- the loop ------------------------------------------------------------
     def _new_engine(self, ncells, ngenes, **options):
         factory = _engine_factory or CaviEngine
+        if FP32_SWEEP and np.dtype(self.dtype) == np.float32:
+            # float32 models (scHPF_.py:225-246 `dtype`): the sweeps run in fp32 like the reference's
+            # float32 numba kernels; the state and the rate / digamma updates stay fp64
+            options.setdefault("precision", 32)
         if isinstance(self.device, (list, tuple)):
             if len(self.device) > 1:
                 # several GPUs from this one process: cells sharded over them (schpf_b200/multi.py)

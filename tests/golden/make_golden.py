@@ -31,6 +31,8 @@ Fixtures
   trials_small.npz  run_trials: three seeded restarts (final losses in return order, the best model)
                     and two restarts scored on projected validation cells.
   fp32_small.npz    the same loop with dtype=np.float32 (mixed precision in the reference).
+  fp32_k20.npz      dtype=np.float32 at K = 20 (600 x 900), 20 iterations, next to the reference's
+                    float64 run from the same init (the float32 noise of the reference itself).
 """
 import os
 import sys
@@ -276,9 +278,39 @@ def fp32_small():
     print("fp32_small: loss", m.loss, out["dtypes"])
 
 
+def fp32_k20():
+    """dtype=np.float32 at the headline K: 20 iterations of the reference's float32 run from a seeded
+    fp32 init (`fin_`), and the reference's float64 run from the SAME (fp32-valued) init (`f64_`): the
+    distance between the two is the float32 noise of the reference itself, which bounds what a
+    second float32 implementation can be asked to reproduce."""
+    X = synth_coo(600, 900, 80, 20, seed=9)
+    np.random.seed(77)
+    m = scHPF(20, verbose=False, dtype=np.float32)
+    m._initialize(X)
+    out = dict(row=X.row.astype(np.int32), col=X.col.astype(np.int32),
+               data=X.data.astype(np.int32), shape=np.array(X.shape), seed=77,
+               a=m.a, ap=m.ap, bp=m.bp, c=m.c, cp=m.cp, dp=m.dp)
+    out.update(state_dict(m, "init_"))
+    gam = lambda d: schpf.HPF_Gamma(d.vi_shape.astype(np.float64), d.vi_rate.astype(np.float64))
+    m64 = scHPF(20, verbose=False, bp=float(m.bp), dp=float(m.dp), xi=gam(m.xi), theta=gam(m.theta),
+                eta=gam(m.eta), beta=gam(m.beta))
+    m.fit(X, reinit=False, min_iter=20, max_iter=20, check_freq=5, verbose=False)
+    out.update(state_dict(m, "fin_"))
+    out["loss"] = np.array(m.loss)
+    m64.fit(X, reinit=False, min_iter=20, max_iter=20, check_freq=5, verbose=False)
+    out.update(state_dict(m64, "f64_"))
+    out["f64_loss"] = np.array(m64.loss)
+    rel = lambda a, b: float(np.max(np.abs(a.astype(np.float64) - b) / np.abs(b)))
+    noise = {n: rel(out["fin_" + n], out["f64_" + n]) for n in ("theta_shp", "theta_rte", "beta_shp", "beta_rte", "xi_rte", "eta_rte")}
+    out["f32_vs_f64_max_rel"] = np.array([noise[k] for k in sorted(noise)])
+    np.savez_compressed(os.path.join(HERE, "fp32_k20.npz"), **out)
+    print("fp32_k20: loss", m.loss, "f64 loss", m64.loss, "\n  reference float32 vs float64, max rel:", noise)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (kernels_k4, cavi_cfg1, cavi_k20, reinit_small, simul_small, minibatch_small, trials_small, fp32_small):
+    for fn in (kernels_k4, cavi_cfg1, cavi_k20, reinit_small, simul_small, minibatch_small, trials_small, fp32_small,
+               fp32_k20):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):
