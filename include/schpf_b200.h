@@ -118,8 +118,10 @@ int schpf_destroy(schpf_engine_t *h);
  * "packed_entries" (1 = 4-byte stream entries when every count is < 2^19: half the
  * resident layout, slightly slower sweeps), "overlap_exchange" (default 1: with an attached
  * communicator schpf_step runs the all-reduce on a second stream underneath the cells-own sweep;
- * 0 = in order on the engine's stream), "lanes" (default 1: K in 13..20 and 29..32 run the
- * one-lane-per-owner sweep; 0 = lane-pair sweep for every K), "rank_per_range" (-1 automatic) */
+ * 0 = in order on the engine's stream), "lanes" (default 1: K <= 20 and 29..32 run the
+ * one-lane-per-owner sweep; 0 = lane-pair sweep for every K), "rank_per_range" (-1 automatic),
+ * "precision" (64 default; 32 = the fp32 sweep used for dtype=np.float32 models, scHPF_.py:225-246:
+ * table entries, dot product, quotient and per-panel sums in fp32, everything else fp64) */
 int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value);
 
 /* The sparse count matrix as COO triples (X.row, X.col, X.data of a
@@ -212,13 +214,32 @@ int schpf_xphi_debug(schpf_engine_t *h, double *out_host_nnz_x_K);
 int schpf_layout_dump(schpf_engine_t *h, int side, int64_t capacity, int32_t *own, int32_t *oth,
                       int32_t *count, int64_t *n_out);
 
+/* ---- device-side ingest of the text formats the reference loads before a fit ----------------------
+ * Replaces `scipy.io.mmread` (bin/scHPF:373-374; files written by `scHPF prep`, bin/scHPF:327,361) and
+ * `load_coo` (schpf/preprocessing.py:11-29: np.loadtxt of "row<TAB>col<TAB>count" lines) for the
+ * data lines; the host reads the few header lines and passes the offset of the first data byte.
+ * `d_text` is the file's bytes in device memory.  Data lines = non-empty lines not starting with '%'.
+ * Output order = file order (what mmread / loadtxt return).
+ *   schpf_count_lines   how many data lines d_text[begin, nbytes) holds.
+ *   schpf_parse_triples nfields 3: "row col count" (a count may be written as a real with zero
+ *                       fraction, e.g. 3.000e+00), 2: "row col" with count 1 (MatrixMarket `pattern`);
+ *                       index_base 1 (MatrixMarket) or 0 (the tsv); outputs are device int32 arrays of
+ *                       `capacity` elements; *n_out = lines parsed.  A malformed line (non-integer or
+ *                       negative field, index below the base, value >= 2^31, extra fields) returns
+ *                       SCHPF_ERR_ARG with its byte offset in *err_offset. */
+int schpf_count_lines(int device, void *stream, const char *d_text, int64_t nbytes, int64_t begin, int64_t *n_lines);
+int schpf_parse_triples(int device, void *stream, const char *d_text, int64_t nbytes, int64_t begin, int nfields,
+                        int index_base, int32_t *d_row, int32_t *d_col, int32_t *d_val, int64_t capacity,
+                        int64_t *n_out, int64_t *err_offset);
+
 /* wait for all enqueued work of this handle */
 int schpf_synchronize(schpf_engine_t *h);
 
 /* counters: what = "nnz", "padded_nnz_cells", "padded_nnz_genes",
  * "sweep_launches", "shape_sweep_launches", "kernel_launches", "sweep_ms" / "sweep_ms_shape" /
  * "sweep_ms_llh" (need option timing=1; synchronise), "iterations", "slow_path_hits",
- * "layout_bytes", "panel_rows", "warps_per_cta", "lanes" (1 = one-lane-per-owner sweep) */
+ * "layout_bytes", "panel_rows", "warps_per_cta", "lanes" (1 = one-lane-per-owner sweep),
+ * "precision" (32 = fp32 sweep, option "precision" before schpf_set_coo; 64 otherwise) */
 int schpf_counter(schpf_engine_t *h, const char *what, double *value);
 
 #ifdef __cplusplus

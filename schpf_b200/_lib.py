@@ -60,6 +60,9 @@ SIGNATURES = {
     "schpf_llh_pointwise": [c_vp, p_dbl],
     "schpf_xphi_debug": [c_vp, p_dbl],
     "schpf_layout_dump": [c_vp, c_int, c_i64, p_i32, p_i32, p_i32, ctypes.POINTER(c_i64)],
+    "schpf_count_lines": [c_int, c_vp, c_vp, c_i64, c_i64, ctypes.POINTER(c_i64)],
+    "schpf_parse_triples": [c_int, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_i64,
+                            ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)],
     "schpf_synchronize": [c_vp],
     "schpf_counter": [c_vp, ctypes.c_char_p, p_dbl],
 }
@@ -104,8 +107,15 @@ def as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def to_host(a):
+    """numpy view of a host array, or a host copy of a CUDA tensor (io.DeviceCOO fields)"""
+    if hasattr(a, "is_cuda"):
+        return a.cpu().numpy()
+    return np.asarray(a)
+
+
 def as_i32(a, what="index"):
-    a = np.asarray(a)
+    a = to_host(a)
     if a.dtype != np.int32:
         if a.size and (a.min() < np.iinfo(np.int32).min or a.max() > np.iinfo(np.int32).max):
             raise ValueError("%s values do not fit int32" % what)

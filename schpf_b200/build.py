@@ -15,7 +15,7 @@ SRC_DIR = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("SCHPF_BUILD_TAG", "")
 OUT_DIR = os.path.join(HERE, "_C" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(OUT_DIR, "libschpf_b200.so")
-SOURCES = ["engine.cu", "sweep.cu", "sweep_lanes.cu", "sweep_f32.cu", "layout.cu", "dense.cu", "shims.cu"]
+SOURCES = ["engine.cu", "sweep.cu", "sweep_lanes.cu", "sweep_f32.cu", "layout.cu", "ingest.cu", "dense.cu", "shims.cu"]
 HEADERS = [os.path.join(SRC_DIR, "common.cuh"),
            os.path.join(HERE, "..", "include", "schpf_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -70,6 +70,8 @@ def _random_phi_step(engine, data, nfactors, rng=np.random, **flags):
     nnz = data.shape[0]
     if nnz * nfactors <= HOST_DIRICHLET_LIMIT:
         random_phi = rng.dirichlet(np.ones(nfactors), nnz)
+        if hasattr(data, "is_cuda"):            # io.DeviceCOO: the counts live on the device
+            data = data.cpu().numpy()
         engine.step_with_xphi(data[:, None] * random_phi, **flags)
     else:
         engine.step_random_phi(int(rng.randint(0, 2 ** 31 - 1)), **flags)

@@ -153,10 +153,12 @@ __host__ __device__ __forceinline__ int64_t tab_index(const TabGeom &g, int64_t 
 {
     return k < g.KA ? i * g.KA + k : g.offB + i * g.KB + (k - g.KA);
 }
-// padded row length of the one-lane kernel's classes: K 13..16 -> 16, 17..20 -> 20, 29..32 -> 32 (else unsupported)
+// padded row length of the one-lane kernel's classes: K <= 16 -> 16, 17..20 -> 20, 29..32 -> 32 (else unsupported).
+// K <= 12 runs the 16-wide kernel on zero columns: measured on cfg-3 (profiles/r2e_bench_K*.json) the lane-pair
+// kernel takes 2.10 (K=7) and 2.31 ms (K=10) per sweep pair, the 16-wide one-lane kernel 2.02 whatever K is.
 __host__ __device__ constexpr int lanes_kp_of(int K)
 {
-    return (K >= 13 && K <= 16) ? 16 : (K >= 17 && K <= 20) ? 20 : (K >= 29 && K <= 32) ? 32 : 0;
+    return (K >= 1 && K <= 16) ? 16 : (K >= 17 && K <= 20) ? 20 : (K >= 29 && K <= 32) ? 32 : 0;
 }
 
 // y as the HIGH WORD of its double: counts below 2^21 have an all-zero low word, so the sweep

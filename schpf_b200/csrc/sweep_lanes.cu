@@ -19,7 +19,7 @@
 //            (0,1), odd lanes (1,0); the layout's 4x4 edge colouring (layout.cu) guarantees that
 //            the 4 even lanes of a quarter warp read rows of 4 different residues mod 4 at every
 //            step, and likewise the 4 odd lanes -> 8 different bank groups.
-// K in {13..16} is NA=1, REM=0; {17..20} NA=1, REM=1; {29..32} NA=2, REM=0: with REM = 0 the
+// K <= 16 is NA=1, REM=0 (zero columns beyond K); {17..20} NA=1, REM=1; {29..32} NA=2, REM=0: with REM = 0 the
 // stream needs no bank schedule at all.
 //
 // Epilogue: the accumulators are staged in shared memory in natural order and added to the
@@ -47,7 +47,7 @@ namespace {
 #define LANES_NS20 2
 #endif
 #ifndef LANES_NS32
-#define LANES_NS32 1
+#define LANES_NS32 2      // measured K=30, cfg-3: two steps per block 4.00 ms per sweep pair, one 4.43 (254 registers, 8 warps)
 #endif
 #ifndef LANES_BULK_RED
 #define LANES_BULK_RED 1
@@ -457,7 +457,7 @@ int dispatch_lanes(int KP, const SideLayout &L, const SweepArgs &args, cudaStrea
 
 }  // namespace
 
-// K classes served by the one-lane-per-owner kernel: KP = 16 (K 13..16), 20 (17..20), 32 (29..32)
+// K classes served by the one-lane-per-owner kernel: KP = 16 (K <= 16), 20 (17..20), 32 (29..32)
 bool lanes_supported(int K)
 {
     const int kp = lanes_kp_of(K);

@@ -55,7 +55,8 @@ class LocalShardedEngine(object):
             e.set_option(key, value)
 
     def set_coo(self, row, col, data):
-        row, col, data = (np.asarray(a) for a in (row, col, data))
+        from ._lib import to_host
+        row, col, data = (to_host(a) for a in (row, col, data))      # shards are cut on the host
         world = len(self.devices)
         self.nnz = int(row.shape[0])
         self.bounds = shard_bounds_by_nnz(np.bincount(row, minlength=self.ncells), world)
