@@ -497,6 +497,7 @@ def main():
     ap.add_argument("--target-ctas", type=int, default=0)
     ap.add_argument("--precision", type=int, default=64, choices=[32, 64],
                     help="32: the fp32 sweep that float32 models use (a separate line, never the headline)")
+    ap.add_argument("--packed", type=int, default=-1, help="4-byte stream entries: -1 automatic, 0 wide entries")
     ap.add_argument("--lanes", type=int, default=1, help="0: lane-pair sweep for every K (round-1 kernels)")
     ap.add_argument("--rank-per-range", type=int, default=-1, help="owners re-ranked inside every panel range (-1 auto)")
     ap.add_argument("--free-schedule", type=int, default=-1, help="K 17..20: plane B without the bank schedule (-1 auto)")
@@ -529,9 +530,14 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
+    bound = 0
     if world > 1:
+        # one process per GPU: stay on the cores (and the memory) of this GPU's NUMA node
+        from schpf_b200.engine import bind_host_to_device
+        if not os.environ.get("SCHPF_BENCH_NO_BIND"):
+            bound = bind_host_to_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(device))
-    log("process group up")
+    log("process group up (bound to %d cores)" % bound)
 
     def barrier():
         if world > 1:
@@ -551,6 +557,8 @@ def main():
     f32 = args.precision == 32
     if f32:
         opts["precision"] = 32
+    if args.packed >= 0:
+        opts["packed_entries"] = args.packed
     if args.rank_per_range >= 0:
         opts["rank_per_range"] = args.rank_per_range
     if args.free_schedule >= 0:
@@ -658,7 +666,7 @@ def main():
     launches = local.counter("kernel_launches")
     lanes = bool(local.counter("lanes"))
     info = {k: local.counter(k) for k in ("padded_nnz_cells", "padded_nnz_genes", "panel_rows", "grid_cells",
-                                          "grid_genes", "layout_bytes", "slow_path_hits", "warps_per_cta")}
+                                          "grid_genes", "layout_bytes", "slow_path_hits", "warps_per_cta", "packed_entries")}
     info["lanes_kernel"] = lanes
 
     # ---- roofline of the dominant kernel: the two shape sweeps of an iteration --
@@ -688,7 +696,7 @@ def main():
         "iters_per_sec": steps / (total_ms * 1e-3),
         "config": {"workload": workload, "nnz_total": nnz_total, "nnz_per_gpu": nnz_local, "check_freq": cf,
                    "l2_policy": "inputs_exceed_L2 (entry streams %.1f GB per sweep vs 126 MB L2)" %
-                                (info["padded_nnz_cells"] * 8 / 1e9),
+                                (info["padded_nnz_cells"] * (4 if info["packed_entries"] else 8) / 1e9),
                    "parallelism": ("cells sharded over %d GPU(s); one NCCL all-reduce of G*K+K doubles per iteration, %s"
                                    % (world, "torch.distributed" if args.torch_exchange else
                                       "issued by the engine in order on its stream" if args.no_overlap else

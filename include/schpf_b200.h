@@ -115,8 +115,9 @@ int schpf_destroy(schpf_engine_t *h);
 /* tuning knobs, before schpf_set_coo: "panel_rows", "warps_per_cta",
  * "target_ctas", "variant" (0 = tiled two-pass sweep, 1 = literal per-nnz
  * kernel with atomics), "timing" (1 = record CUDA events around the sweeps),
- * "packed_entries" (1 = 4-byte stream entries when every count is < 2^19: half the
- * resident layout, slightly slower sweeps), "overlap_exchange" (default 1: with an attached
+ * "packed_entries" (4-byte stream entries pad<<31 | count<<12 | row when every count is < 2^19: half the
+ * entry stream and resident layout; -1 default = where it is not slower (one-lane K <= 16 and the fp32
+ * sweep), 0 = never, 1 = wherever the stream allows it), "overlap_exchange" (default 1: with an attached
  * communicator schpf_step runs the all-reduce on a second stream underneath the cells-own sweep;
  * 0 = in order on the engine's stream), "lanes" (default 1: K <= 20 and 29..32 run the
  * one-lane-per-owner sweep; 0 = lane-pair sweep for every K), "rank_per_range" (-1 automatic),

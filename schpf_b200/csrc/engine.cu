@@ -142,7 +142,7 @@ struct schpf_engine {
     int opt_target_ctas = 4736; // 148 SMs x 2 CTAs x 16 waves
     int opt_variant = 0;
     int opt_timing = 0;
-    int opt_packed_entries = 0; // 1 = 4-byte stream entries when every count is < 2^19
+    int opt_packed_entries = -1; // 4-byte stream entries when every count is < 2^19: -1 = one-lane streams only, 0 = never, 1 = lane pairs too
     int opt_lanes = 1;          // 0 = lane-pair kernels for every K (sweep.cu)
     int opt_precision = 64;     // 32 = fp32 sweep for float32 models (sweep_f32.cu); state and updates stay fp64
     int opt_rank_per_range = -1; // -1 = automatic (on for streams without a bank schedule); 0 / 1
@@ -198,6 +198,9 @@ struct schpf_engine {
 
 namespace {
 
+#ifndef LANES_PACKED_DEFAULT
+#define LANES_PACKED_DEFAULT 1
+#endif
 #ifndef LANES_FREE20_DEFAULT
 #define LANES_FREE20_DEFAULT 1
 #endif
@@ -588,11 +591,20 @@ int finish_coo(schpf_engine *h)
         if (h->opt_rank_per_range != 0) lflags |= LAYOUT_RANK_PER_RANGE | LAYOUT_SINGLE_PANEL_RANGES;
     }
     trace_mark(h->stream, "validate + tables");
-    // 4-byte entries are possible when every count fits 19 bits (flag bit 8 = some count >= 2^19).
-    // Measured on cfg-3 they are SLOWER than 8-byte entries (3.61 vs 3.43 ms per sweep pair: the
-    // sweep is not HBM-bound and the decode costs issue slots), so they are opt-in: they halve
-    // the resident layout (1.8 GB instead of 3.6 GB at 1.9e8 nnz) when memory matters.
-    const bool packed = !h->lanes && !h->f32 && h->opt_packed_entries && !(flag & 8) && Po <= (1 << PACKED_ROW_BITS);
+    // 4-byte entries (common.cuh pack_entry) are possible when every count fits 19 bits (flag bit 8 = some
+    // count >= 2^19) and a panel has at most 2^12 rows; they halve the entry stream and the resident layout.
+    // Measured on cfg-3, sweep pair packed / wide (gpurun_out/r2o_*, r2m_*; decode at the point of use):
+    //   one-lane K <= 16   1.98 / 2.02 ms   fp32 (any K)  1.93 / 1.94, 1.90 / 1.92   -> packed by default
+    //   one-lane K 17..20  2.47 / 2.41      K 29..32      4.40 / 4.01 (the I2F.F64 of the count lands on the
+    //   fp64 pipe these kernels are short of; wide entries carry the count as the high word of its double)
+    //   lane pairs (round 1) 3.61 / 3.43                                                 -> wide by default
+    // "packed_entries": -1 = these defaults, 0 = always wide, 1 = packed wherever the stream allows it.
+    const bool lane_stream = (h->lanes || h->f32) && (lflags & LAYOUT_FREE);
+    const bool packed_by_default = LANES_PACKED_DEFAULT && lane_stream && (h->f32 || lanes_kp_of(h->K) == 16);
+    const bool want_packed = h->opt_packed_entries == 1 ? (lane_stream || !(h->lanes || h->f32))
+                                                        : h->opt_packed_entries < 0 && packed_by_default;
+    const bool packed = want_packed && !(flag & 8) && Po <= (1 << PACKED_ROW_BITS);
+    if (packed) lflags &= ~LAYOUT_YHI;
     RC_TRY(build_side_layout(h->cells, h->stream, h->nnz, h->row, h->col, h->data, h->C, h->G, Po, warps,
                              h->opt_target_ctas, packed, opw, lflags));
     trace_mark(h->stream, "layout cells total");

@@ -261,8 +261,11 @@ __global__ void place_entries_kernel(int64_t n_qw, int npanel, int opw, bool fre
             for (int step = 0; step < cnt_o; ++step) {
                 const int64_t dst = ((pair0 + (step >> 1)) * opw + pos) * 2 + (step & 1);
                 const uint64_t v = vals[src0 + step];
-                reinterpret_cast<int2 *>(entries_v)[dst] =
-                    make_int2((int)(uint32_t)v, count_field((uint32_t)(v >> 32), yhi));
+                if (PACKED)
+                    reinterpret_cast<uint32_t *>(entries_v)[dst] = pack_entry((uint32_t)v, (uint32_t)(v >> 32), false);
+                else
+                    reinterpret_cast<int2 *>(entries_v)[dst] =
+                        make_int2((int)(uint32_t)v, count_field((uint32_t)(v >> 32), yhi));
             }
         }
         return;
@@ -450,8 +453,8 @@ int build_side_layout(SideLayout &L, cudaStream_t stream, int64_t nnz, const int
         set_error("layout: owners per warp must be 16 or 32, got %d", opw);
         return SCHPF_ERR_ARG;
     }
-    if (packed && (opw != GROUPS_PER_WARP || free_mode || yhi)) {
-        set_error("layout: packed entries exist for the lane-pair stream only");
+    if (packed && (yhi || (opw == 32 && !free_mode))) {
+        set_error("layout: packed entries exist for the lane-pair stream and for the schedule-free one-lane stream");
         return SCHPF_ERR_ARG;
     }
     L.packed = packed;

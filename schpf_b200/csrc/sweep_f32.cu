@@ -65,12 +65,27 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int NP, int MODE>
+// one stream element (two steps of a lane) as {row, pad<<31 | count, row, pad<<31 | count}; PACKED:
+// 4-byte entries pad<<31 | count<<12 | row (common.cuh pack_entry)
+template <bool PACKED>
+__device__ __forceinline__ int4 ld_elem(const char *p)
+{
+    if (PACKED) {
+        const int2 w = ld_stream_int2(reinterpret_cast<const int2 *>(p));
+        constexpr int RM = (1 << PACKED_ROW_BITS) - 1, CM = (1 << PACKED_COUNT_BITS) - 1;
+        return make_int4(w.x & RM, (w.x & (int)0x80000000) | ((w.x >> PACKED_ROW_BITS) & CM), w.y & RM,
+                         (w.y & (int)0x80000000) | ((w.y >> PACKED_ROW_BITS) & CM));
+    }
+    return ld_stream_int4(reinterpret_cast<const int4 *>(p));
+}
+
+template <int NP, int MODE, bool PACKED>
 __global__ void __launch_bounds__(F32Cfg<NP>::WARPS * 32, 1)
 lane_sweep_f32_kernel(const SweepArgs A)
 {
     using Cfg = F32Cfg<NP>;
     constexpr int KF = Cfg::KF, NS = Cfg::NS;
+    constexpr int ES = PACKED ? 8 : 16;           // bytes of one stream element
     constexpr int ROWB = KF * 4;                  // bytes per table row (128 * NP)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -197,21 +212,21 @@ lane_sweep_f32_kernel(const SweepArgs A)
         // this warp's segment of the stream: n elements (two steps each) of 32 lanes
         const int64_t i0 = sp[p];
         const int n = (int)(sp[p + 1] - i0);
-        const int4 *ptr = reinterpret_cast<const int4 *>(A.entries) + i0 * 32 + lane;
+        const char *ptr = reinterpret_cast<const char *>(A.entries) + (i0 * 32 + lane) * ES;
         int4 cur = make_int4(0, 0, 0, 0), nxt = cur;
-        if (n > 0) cur = ld_stream_int4(ptr);
-        if (n > 1) nxt = ld_stream_int4(ptr + 32);
+        if (n > 0) cur = ld_elem<PACKED>(ptr);
+        if (n > 1) nxt = ld_elem<PACKED>(ptr + 32 * ES);
         const int oth0 = p * A.panel_rows;
         mbar_wait(mbar, parity);
         parity ^= 1u;
 
         int j = 0;
-        for (; j + 1 < n; j += 2, ptr += 64) {
-            prefetch_l2(ptr + 8 * 64);
-            prefetch_l2(ptr + 8 * 64 + 32);
+        for (; j + 1 < n; j += 2, ptr += 64 * ES) {
+            prefetch_l2(ptr + 8 * 64 * ES);
+            prefetch_l2(ptr + (8 * 64 + 32) * ES);
             const int4 c0 = cur, c1 = nxt;
-            if (j + 2 < n) cur = ld_stream_int4(ptr + 64);
-            if (j + 3 < n) nxt = ld_stream_int4(ptr + 96);
+            if (j + 2 < n) cur = ld_elem<PACKED>(ptr + 64 * ES);
+            if (j + 3 < n) nxt = ld_elem<PACKED>(ptr + 96 * ES);
             if constexpr (NS == 2) {
                 {
                     const int ex[2] = {c0.x, c0.z}, ey[2] = {c0.y, c0.w};
@@ -292,17 +307,17 @@ lane_sweep_f32_kernel(const SweepArgs A)
     }
 }
 
-template <int NP, int MODE>
-int launch_f32(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
+template <int NP, int MODE, bool PACKED>
+int launch_f32_enc(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
 {
     using Cfg = F32Cfg<NP>;
     const size_t smem = f32_sweep_smem_bytes(args.K, L.panel_rows, L.warps);
     static bool configured = false;   // per instantiation
     static size_t configured_smem = 0;
     if (!configured || smem > configured_smem) {
-        CUDA_TRY(cudaFuncSetAttribute(lane_sweep_f32_kernel<NP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(lane_sweep_f32_kernel<NP, MODE, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(lane_sweep_f32_kernel<NP, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        CUDA_TRY(cudaFuncSetAttribute(lane_sweep_f32_kernel<NP, MODE, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
         configured = true;
         configured_smem = smem;
@@ -313,7 +328,7 @@ int launch_f32(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
         set_error("fp32 sweep: warps_per_cta must be in [1, %d] for K=%d", Cfg::WARPS, args.K);
         return SCHPF_ERR_ARG;
     }
-    lane_sweep_f32_kernel<NP, MODE><<<grid, L.warps * 32, smem, stream>>>(args);
+    lane_sweep_f32_kernel<NP, MODE, PACKED><<<grid, L.warps * 32, smem, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("lane_sweep_f32_kernel<planes=%d,mode=%d> launch (grid %d, block %d, smem %zu) -> %s", NP, MODE, grid,
@@ -321,6 +336,12 @@ int launch_f32(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
         return SCHPF_ERR_CUDA;
     }
     return SCHPF_OK;
+}
+
+template <int NP, int MODE>
+int launch_f32(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
+{
+    return L.packed ? launch_f32_enc<NP, MODE, true>(L, args, stream) : launch_f32_enc<NP, MODE, false>(L, args, stream);
 }
 
 }  // namespace

@@ -92,6 +92,8 @@ __device__ __forceinline__ void bulk_red_add_f64(double *dst_gmem, uint32_t src_
 template <bool YHI>
 __device__ __forceinline__ double entry_count(int field)
 {
+    // (the 2^52 + count trick -- one DADD instead of I2F.F64 -- was measured: it costs two more registers
+    // per step and the 168-register K=20 kernel then spills 176 bytes in the loop: 5.6 ms per sweep pair)
     return YHI ? __hiloint2double(field, 0) : (double)(field & 0x7fffffff);
 }
 
@@ -100,10 +102,39 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int NA, int REM, int MODE, bool YHI>
+// One stream element (two steps of a lane) decoded to {row, count field, row, count field}.
+// ENC 0: wide, integer count; 1: wide, count as the high word of its double; 2: packed 4-byte
+// entries pad<<31 | count<<12 | row (common.cuh pack_entry) -- half the stream bytes; the count
+// field comes out as pad<<31 | count like the wide integer encoding.
+constexpr int ENC_WIDE = 0, ENC_YHI = 1, ENC_PACKED = 2;
+// Packed elements stay RAW in their two registers ({w0, w0, w1, w1}: the compiler keeps one copy) until
+// process() decodes them at the point of use, so the loads issued a trip ahead hold two registers, not four.
+template <int ENC>
+__device__ __forceinline__ int4 ld_elem(const char *p)
+{
+    if (ENC == ENC_PACKED) {
+        const int2 w = ld_stream_int2(reinterpret_cast<const int2 *>(p));
+        return make_int4(w.x, w.x, w.y, w.y);
+    }
+    return ld_stream_int4(reinterpret_cast<const int4 *>(p));
+}
+template <int ENC>
+__device__ __forceinline__ int elem_row(int x)
+{
+    return ENC == ENC_PACKED ? (x & ((1 << PACKED_ROW_BITS) - 1)) : x;
+}
+template <int ENC>
+__device__ __forceinline__ int elem_field(int y)       // pad<<31 | count
+{
+    return ENC == ENC_PACKED ? ((y & (int)0x80000000) | ((y >> PACKED_ROW_BITS) & ((1 << PACKED_COUNT_BITS) - 1))) : y;
+}
+
+template <int NA, int REM, int MODE, int ENC>
 __global__ void __launch_bounds__(LaneCfg<NA, REM>::WARPS * 32, LANES_CTAS)
 lane_sweep_kernel(const SweepArgs A)
 {
+    constexpr bool YHI = ENC == ENC_YHI;
+    constexpr int ES = ENC == ENC_PACKED ? 8 : 16;      // bytes of one stream element
     using Cfg = LaneCfg<NA, REM>;
     constexpr int KA = Cfg::KA, KB = Cfg::KB, KP = Cfg::KP;
     constexpr int ROWA = KA * 8;                  // bytes per plane-A row (128 * NA)
@@ -165,10 +196,16 @@ lane_sweep_kernel(const SweepArgs A)
     const int64_t *sp = A.seg_ptr + (int64_t)wg * (A.npanel + 1);
 
     // NS steps of this lane as one straight-line block.  `oth0` = global row of the panel's row 0.
-    auto process = [&](auto ns_tag, const int *ex, const int *ey, int oth0) {
+    auto process = [&](auto ns_tag, const int *ex_raw, const int *ey_raw, int oth0) {
         constexpr int NS = decltype(ns_tag)::value;
         double bv[NS][KP], s[NS];
         bool slow = false;
+        int ex[NS], ey[NS];
+#pragma unroll
+        for (int e = 0; e < NS; ++e) {
+            ex[e] = elem_row<ENC>(ex_raw[e]);
+            ey[e] = elem_field<ENC>(ey_raw[e]);
+        }
 #if LANES_EXP == 2
 #pragma unroll
         for (int e = 0; e < NS; ++e)
@@ -266,10 +303,10 @@ lane_sweep_kernel(const SweepArgs A)
         // this warp's segment of the stream: n elements (two steps each) of 32 lanes
         const int64_t i0 = sp[p];
         const int n = (int)(sp[p + 1] - i0);
-        const int4 *ptr = reinterpret_cast<const int4 *>(A.entries) + i0 * 32 + lane;
+        const char *ptr = reinterpret_cast<const char *>(A.entries) + (i0 * 32 + lane) * ES;
         int4 cur = make_int4(0, 0, 0, 0), nxt = cur;
-        if (n > 0) cur = ld_stream_int4(ptr);
-        if (n > 1) nxt = ld_stream_int4(ptr + 32);
+        if (n > 0) cur = ld_elem<ENC>(ptr);
+        if (n > 1) nxt = ld_elem<ENC>(ptr + 32 * ES);
         const int oth0 = p * A.panel_rows;
         mbar_wait(mbar, parity);
         parity ^= 1u;
@@ -278,9 +315,9 @@ lane_sweep_kernel(const SweepArgs A)
         // trip's arithmetic starts (a whole trip = four steps of latency cover), and the lines of the
         // trip LANES_L2_AHEAD ahead are asked into L2.
         int j = 0;
-        for (; j + 1 < n; j += 2, ptr += 64) {
-            prefetch_l2(ptr + LANES_L2_AHEAD * 64);            // immediate offsets from the lane's own pointer:
-            prefetch_l2(ptr + LANES_L2_AHEAD * 64 + 32);       // no predicate, no extra registers
+        for (; j + 1 < n; j += 2, ptr += 64 * ES) {
+            prefetch_l2(ptr + LANES_L2_AHEAD * 64 * ES);             // immediate offsets from the lane's own pointer:
+            prefetch_l2(ptr + (LANES_L2_AHEAD * 64 + 32) * ES);      // no predicate, no extra registers
 #if LANES_PREFETCH == 0
             // variant: an element is reloaded right after its last use (no copies, two steps of
             // cover: enough for an L2 hit, which the prefetch above is there to make it)
@@ -289,18 +326,18 @@ lane_sweep_kernel(const SweepArgs A)
                     const int ex[2] = {cur.x, cur.z}, ey[2] = {cur.y, cur.w};
                     process(Steps2{}, ex, ey, oth0);
                 }
-                if (j + 2 < n) cur = ld_stream_int4(ptr + 64);
+                if (j + 2 < n) cur = ld_elem<ENC>(ptr + 64 * ES);
                 {
                     const int ex[2] = {nxt.x, nxt.z}, ey[2] = {nxt.y, nxt.w};
                     process(Steps2{}, ex, ey, oth0);
                 }
-                if (j + 3 < n) nxt = ld_stream_int4(ptr + 96);
+                if (j + 3 < n) nxt = ld_elem<ENC>(ptr + 96 * ES);
                 continue;
             }
 #endif
             const int4 c0 = cur, c1 = nxt;
-            if (j + 2 < n) cur = ld_stream_int4(ptr + 64);
-            if (j + 3 < n) nxt = ld_stream_int4(ptr + 96);
+            if (j + 2 < n) cur = ld_elem<ENC>(ptr + 64 * ES);
+            if (j + 3 < n) nxt = ld_elem<ENC>(ptr + 96 * ES);
             if constexpr (Cfg::NS == 2) {
                 {
                     const int ex[2] = {c0.x, c0.z}, ey[2] = {c0.y, c0.w};
@@ -404,7 +441,7 @@ lane_sweep_kernel(const SweepArgs A)
     }
 }
 
-template <int NA, int REM, int MODE, bool YHI>
+template <int NA, int REM, int MODE, int YHI>
 int launch_lanes_y(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
 {
     using Cfg = LaneCfg<NA, REM>;
@@ -438,8 +475,9 @@ int launch_lanes_y(const SideLayout &L, const SweepArgs &args, cudaStream_t stre
 template <int NA, int REM, int MODE>
 int launch_lanes(const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
 {
-    return L.yhi ? launch_lanes_y<NA, REM, MODE, true>(L, args, stream)
-                 : launch_lanes_y<NA, REM, MODE, false>(L, args, stream);
+    return L.packed ? launch_lanes_y<NA, REM, MODE, ENC_PACKED>(L, args, stream)
+           : L.yhi  ? launch_lanes_y<NA, REM, MODE, ENC_YHI>(L, args, stream)
+                    : launch_lanes_y<NA, REM, MODE, ENC_WIDE>(L, args, stream);
 }
 
 template <int MODE>

@@ -273,6 +273,33 @@ def shard_coo_rows(X, rank, world_size):
     return local, lo, hi
 
 
+def bind_host_to_device(device):
+    """Pin the calling process to the CPU cores next to CUDA device `device` (NVML's ideal
+    affinity).  One process per GPU on a multi-socket host: pinned staging buffers allocated
+    afterwards come from the GPU's own NUMA node, so eight ranks uploading their shards at once do
+    not all pull from one socket's memory.  Returns the number of cores bound, 0 when NVML is not
+    usable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = int(device)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            idx = int(vis.split(",")[idx])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cores = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cores &= set(os.sched_getaffinity(0))
+        if not cores:
+            return 0
+        os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:
+        return 0
+
+
 class ShardedEngine(object):
     """Cells sharded over the ranks of a torch.distributed process group.
 

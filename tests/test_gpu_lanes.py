@@ -43,7 +43,8 @@ def _load(e, row, col, data, st):
 @pytest.mark.parametrize("K", [1, 2, 5, 7, 10, 12, 13, 15, 16, 17, 19, 20, 29, 30, 31, 32])
 @pytest.mark.parametrize("opts", [dict(), dict(panel_rows=64), dict(panel_rows=64, rank_per_range=1),
                                   dict(panel_rows=128, rank_per_range=0, warps_per_cta=2),
-                                  dict(panel_rows=64, free_schedule=1), dict(free_schedule=0, rank_per_range=0)])
+                                  dict(panel_rows=64, free_schedule=1), dict(free_schedule=0, rank_per_range=0),
+                                  dict(packed_entries=0), dict(panel_rows=64, packed_entries=0, rank_per_range=0)])
 def test_lane_sweep_against_oracle_and_lane_pairs(K, opts):
     C, G, nnz, n_iter = 517, 389, 24000, 4
     row, col, data, st = _problem(C, G, K, nnz, K)
@@ -120,6 +121,8 @@ def _multiset(a, b, c):
     (20, dict()), (20, dict(panel_rows=64, rank_per_range=1)), (16, dict(panel_rows=64)), (16, dict(rank_per_range=0)),
     (19, dict(panel_rows=64, free_schedule=1)), (20, dict(free_schedule=1, rank_per_range=0)),
     (30, dict(panel_rows=32, warps_per_cta=1)), (50, dict(panel_rows=16)),
+    (20, dict(packed_entries=0)), (16, dict(panel_rows=64, packed_entries=0)), (30, dict(panel_rows=32, packed_entries=0)),
+    (7, dict()),
 ])
 @pytest.mark.parametrize("big", [False, True])
 def test_layout_round_trip_is_exact(K, opts, big):
@@ -138,6 +141,31 @@ def test_layout_round_trip_is_exact(K, opts, big):
             assert np.all(oth[~real] == -1) and np.all(cnt[~real] == 0)
             r, c = (own[real], oth[real]) if side == 0 else (oth[real], own[real])
             assert np.array_equal(_multiset(r, c, cnt[real]), want)
+
+
+@pytest.mark.parametrize("K", [7, 16, 20, 32])
+def test_stream_encoding_follows_the_counts(K):
+    """schedule-free one-lane streams can use 4-byte entries (pad<<31 | count<<12 | row) when every
+    count is below 2^19, wide entries otherwise; both give the same result"""
+    C, G, nnz = 400, 300, 12000
+    out = {}
+    for big, opts, want in ((False, dict(packed_entries=1), 1), (False, dict(packed_entries=0), 0),
+                            (True, dict(packed_entries=1), 0)):
+        row, col, data, st = _problem(C, G, K, nnz, 3, big=big)
+        with CaviEngine(C, G, K, **opts) as e:
+            _load(e, row, col, data, st)
+            assert e.counter("packed_entries") == want
+            e.step(3)
+            out[(big, want)] = (e.get_state(), e.counter("layout_bytes"))
+    assert max_rel(out[(False, 1)][0]["theta"][0], out[(False, 0)][0]["theta"][0]) < 1e-12
+    assert max_rel(out[(False, 1)][0]["beta"][0], out[(False, 0)][0]["beta"][0]) < 1e-12
+    assert out[(False, 1)][1] < out[(False, 0)][1]
+    # defaults: packed where it is not slower (K <= 16, fp32), wide where the count conversion costs fp64 issue slots
+    row, col, data, st = _problem(C, G, K, nnz, 3)
+    for opts, want in ((dict(), 1 if K <= 16 else 0), (dict(precision=32), 1)):
+        with CaviEngine(C, G, K, **opts) as e:
+            e.set_coo(row, col, data)
+            assert e.counter("packed_entries") == want
 
 
 def test_per_panel_ranking_removes_the_padding_of_schedule_free_streams():

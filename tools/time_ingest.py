@@ -55,10 +55,30 @@ def main():
     same = bool(np.array_equal(dev.row.cpu().numpy(), ref.row) and np.array_equal(dev.col.cpu().numpy(), ref.col)
                 and np.array_equal(dev.data.cpu().numpy(), ref.data))
     os.remove(path)
+    # the reference's own tsv loader (preprocessing.py:27-28) on a 2e6-line prefix (np.loadtxt is slow)
+    n_tsv = min(int(X.nnz), 2_000_000)
+    tsv = os.path.join(d, "x.tsv")
+    pd.DataFrame({"r": X.row[:n_tsv], "c": X.col[:n_tsv], "v": X.data[:n_tsv]}).to_csv(tsv, sep="\t", header=False, index=False)
+    sio.load_coo(tsv)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_t = sio.load_coo(tsv)
+    torch.cuda.synchronize()
+    t_tsv = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    raw_t = np.loadtxt(tsv, delimiter="\t", dtype=int)
+    t_loadtxt = time.perf_counter() - t0
+    same_t = bool(np.array_equal(dev_t.row.cpu().numpy(), raw_t[:, 0]) and np.array_equal(dev_t.col.cpu().numpy(), raw_t[:, 1])
+                  and np.array_equal(dev_t.data.cpu().numpy(), raw_t[:, 2]))
+    tsv_bytes = os.path.getsize(tsv)
+    os.remove(tsv)
     print(json.dumps({"file_bytes": size, "nnz": int(X.nnz), "shape": [C, G],
                       "load_mtx_s": t_dev, "of_which_read_and_h2d_s": t_h2d, "of_which_device_parse_s": t_parse,
                       "device_parse_GBps": size / t_parse / 1e9, "scipy_mmread_s": t_ref, "speedup_vs_mmread": t_ref / t_dev,
                       "identical_to_mmread": same,
+                      "tsv": {"lines": n_tsv, "file_bytes": tsv_bytes, "load_coo_s": t_tsv, "np_loadtxt_s": t_loadtxt,
+                              "speedup_vs_loadtxt": t_loadtxt / t_tsv, "identical_to_loadtxt": same_t,
+                              "what": "schpf_b200.io.load_coo vs the reference's load_coo = np.loadtxt(delimiter='\\t', dtype=int) (preprocessing.py:27-28)"},
                       "what": "schpf_b200.io.load_mtx (file -> pageable host -> HBM -> parse on device, file order) vs "
                               "scipy.io.mmread of the same file on the host (bin/scHPF:373-374)"}))
 
