@@ -46,8 +46,12 @@ extern "C" {
 #define SCHPF_SIMULTANEOUS  2   /* beta_theta_simultaneous=True ordering (scHPF_.py:666-684) */
 #define SCHPF_CELLS_FIRST   4   /* minibatch ordering (scHPF_.py:686-704, `batched`): theta/xi are updated
                                    first (from the old beta), and beta's rate then sees the NEW theta.
-                                   Single engine only: with an attached communicator the exchange
-                                   buffer already holds the old theta's column sums -> SCHPF_ERR_ARG. */
+                                   On a sharded engine (a minibatch whose cells are spread over the ranks)
+                                   the exchange therefore happens AFTER the cell update: with an attached
+                                   communicator inside schpf_step / schpf_step_end; split-phase callers use */
+#define SCHPF_PHASE_CELLS   8   /* schpf_step_end(CELLS_FIRST | PHASE_CELLS): theta/xi + the new theta's column
+                                   sums into the exchange buffer; all-reduce the buffer; then ...            */
+#define SCHPF_PHASE_GENES  16   /* ... schpf_step_end(CELLS_FIRST | PHASE_GENES): beta/eta                  */
 
 typedef struct schpf_engine schpf_engine_t;
 

@@ -70,6 +70,8 @@ SIGNATURES = {
 FREEZE_GENES = 1
 SIMULTANEOUS = 2
 CELLS_FIRST = 4
+PHASE_CELLS = 8
+PHASE_GENES = 16
 MAX_FACTORS = 64
 
 _lib = None

@@ -149,11 +149,20 @@ class MinibatchLoop(object):
                        `schpf_copy_cell_state` (D2D, no host synchronisation in the loop).
     The default loss is taken by a full-matrix engine (the master in device mode) that gets
     its layout only if that loss is used.
+
+    With `process_group` (cells sharded over ranks, `X` = this rank's rows): the schedule runs over
+    ALL cells -- rank 0 draws the one shuffle from its numpy stream and broadcasts it, so a seeded run
+    walks the same windows as the unsharded loop -- and every rank takes the cells of a window that
+    it owns (in window order).  theta/xi of those cells are updated locally; beta then needs the
+    sums over the whole batch, so the one exchange of the iteration happens AFTER the cell update
+    (`ShardedEngine.step(cells_first=True)`).  theta/xi stay in host arrays (a rank's part of a
+    window is not a contiguous range of its cells); the loss is the loss over all ranks' cells.
     """
 
     def __init__(self, new_engine, X, hyper, state, nfactors, batchsize, freeze_genes, simultaneous,
-                 device_state=None, rng=np.random):
+                 device_state=None, rng=np.random, process_group=None, shared_seed=None, cell_range=None):
         self.rng = rng
+        self.process_group, self.shared_seed = process_group, shared_seed
         self.new_engine, self.hyper, self.nfactors = new_engine, hyper, nfactors
         self.ncells, self.ngenes = X.shape
         self.batchsize = int(batchsize)
@@ -166,8 +175,13 @@ class MinibatchLoop(object):
         f = lambda pair: [np.array(pair[0], dtype=np.float64, copy=True), np.array(pair[1], dtype=np.float64, copy=True)]
         self.theta, self.xi = f(state["theta"]), f(state["xi"])      # host mode: the live copy
         self._gene_init = dict(beta=state["beta"], eta=state["eta"])
-        self.schedule = MinibatchSchedule(self.ncells, self.batchsize, rng)
-        n_windows = self.ncells // gcd(self.ncells, self.batchsize)
+        # cell_range = (first global cell of this rank, cells of all ranks); unsharded: (0, ncells)
+        self.lo, self.ncells_total = (0, self.ncells) if cell_range is None else (int(cell_range[0]), int(cell_range[1]))
+        self.schedule = MinibatchSchedule(self.ncells_total, self.batchsize, rng)
+        if process_group is not None:
+            self.device_state = False
+            self.schedule.order = self._broadcast_order(process_group, self.ncells_total, rng)
+        n_windows = self.ncells_total // gcd(self.ncells_total, self.batchsize)
         self.cache_engines = n_windows <= MINIBATCH_ENGINE_CACHE
         self.engines = {}          # window start -> engine (only one entry when not caching)
         self.current = None        # the engine holding the newest beta / eta
@@ -175,10 +189,29 @@ class MinibatchLoop(object):
         self.full_has_coo = False
         self.Xp_csr = None         # device mode: rows in shuffled order
 
+    @staticmethod
+    def _broadcast_order(group, ncells_total, rng):
+        """the reference's one shuffle (util.py:220-221), drawn on rank 0, the same on every rank"""
+        import torch.distributed as dist
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        box = [None]
+        if dist.get_rank(group) == 0:
+            order = np.arange(ncells_total)
+            rng.shuffle(order)
+            box = [order]
+        dist.broadcast_object_list(box, src=src, group=group)
+        return np.asarray(box[0])
+
+    def _wrap(self, engine):
+        if self.process_group is None:
+            return engine
+        from .engine import ShardedEngine
+        return ShardedEngine(engine, self.process_group)
+
     # -- engines -------------------------------------------------------------
     def _full_engine(self, with_coo):
         if self.full is None:
-            self.full = self.new_engine(self.ncells, self.ngenes)
+            self.full = self._wrap(self.new_engine(self.ncells, self.ngenes))
             self.full.set_hyper(*self.hyper)
             if self.device_state:
                 order = self.schedule.draw_order()
@@ -203,8 +236,13 @@ class MinibatchLoop(object):
         eng, Xb = self.engines.get(key), None
         if eng is None or not self.cache_engines:
             Xb = self._batch_coo(start, batch_ix)
+            if eng is not None and eng.ncells != len(batch_ix):     # sharded, not cached: this rank's part varies
+                eng.close()
+                eng = None
             if eng is None:
-                eng = self.new_engine(self.batchsize, self.ngenes)
+                # sharded: the device's t == 0 draw is keyed by (row + offset, gene); shift every rank's rows apart
+                opts = {"row_offset": self.lo} if self.process_group is not None else {}
+                eng = self._wrap(self.new_engine(len(batch_ix), self.ngenes, **opts))
                 eng.set_hyper(*self.hyper)
                 self.engines[key] = eng
             eng.set_coo(Xb.row, Xb.col, Xb.data)
@@ -217,6 +255,12 @@ class MinibatchLoop(object):
     def run(self, t, n, reinit):
         for tt in range(t, t + n):
             start, batch_ix = self.schedule.next()
+            if self.process_group is not None:
+                # this rank's cells of the window, in window order, as local row indices
+                batch_ix = batch_ix[(batch_ix >= self.lo) & (batch_ix < self.lo + self.ncells)] - self.lo
+                if batch_ix.shape[0] == 0:
+                    raise ValueError("minibatch window %d holds none of this rank's %d cells: batchsize=%d is too "
+                                     "small for this sharding" % (start, self.ncells, self.batchsize))
             if self.device_state:
                 master = self._full_engine(with_coo=False)
             eng, Xb = self._batch_engine(start, batch_ix)
@@ -228,7 +272,9 @@ class MinibatchLoop(object):
             else:
                 eng.set_state(theta=(self.theta[0][batch_ix], self.theta[1][batch_ix]),
                               xi=(self.xi[0][batch_ix], self.xi[1][batch_ix]))
-            if tt == 0 and reinit:
+            if tt == 0 and reinit and self.process_group is not None:
+                eng.step(1, random_phi_seed=self.shared_seed(self.process_group, self.rng), **self.flags)
+            elif tt == 0 and reinit:
                 if Xb is None:
                     Xb = self._batch_coo(start, batch_ix)
                 _random_phi_step(eng, Xb.data, self.nfactors, self.rng, **self.flags)

@@ -415,14 +415,28 @@ int step_begin_impl(schpf_engine *h, int flags, int mode, uint64_t seed)
     return SCHPF_OK;
 }
 
+// the one exchange step of an iteration, when the engine owns the communicator
+int allreduce_exchange(schpf_engine *h, cudaStream_t stream)
+{
+    return nccl_check(g_nccl.AllReduce(h->exch, h->exch, (size_t)(h->G * h->K + h->K), NCCL_FLOAT64, NCCL_SUM,
+                                       h->comm, stream),
+                      "ncclAllReduce(exchange buffer)");
+}
+
+// the minibatch order exchanges AFTER the cell update (inside step_end_impl), not between the phases
+inline bool exchange_is_late(int flags) { return (flags & SCHPF_CELLS_FIRST) && !(flags & SCHPF_SIMULTANEOUS); }
+
 int step_end_impl(schpf_engine *h, int flags)
 {
     const bool freeze = flags & SCHPF_FREEZE_GENES;
     const bool simultaneous = flags & SCHPF_SIMULTANEOUS;
     const bool cells_first = flags & SCHPF_CELLS_FIRST;
     const int K = h->K;
-    if (cells_first && h->comm && !freeze) {
-        set_error("SCHPF_CELLS_FIRST (minibatch order) is not available on a sharded engine");
+    // split-phase callers of the minibatch order on a sharded engine: PHASE_CELLS = theta/xi and the
+    // new theta's column sums into the exchange buffer, (all-reduce by the caller,) PHASE_GENES = beta/eta
+    const bool only_cells = flags & SCHPF_PHASE_CELLS, only_genes = flags & SCHPF_PHASE_GENES;
+    if ((only_cells || only_genes) && (!cells_first || simultaneous || (only_cells && only_genes))) {
+        set_error("SCHPF_PHASE_CELLS / SCHPF_PHASE_GENES split the SCHPF_CELLS_FIRST order only (one of them per call)");
         return SCHPF_ERR_ARG;
     }
     auto theta_update = [&]() -> int {
@@ -451,10 +465,16 @@ int step_end_impl(schpf_engine *h, int flags)
     } else if (cells_first) {
         // scHPF_.py:686-704 (`batched`): cell updates first, from the OLD beta; beta's rate then sums
         // theta.e_x of the NEW theta, which theta_update has just left in colsum_t_next
-        RC_TRY(theta_update());
+        if (!only_genes) {
+            RC_TRY(theta_update());
+            if (!freeze)
+                CUDA_TRY(cudaMemcpyAsync(h->exch + (size_t)h->G * K, h->colsum_t_next, sizeof(double) * K,
+                                         cudaMemcpyDeviceToDevice, h->stream));
+        }
+        if (only_cells) return SCHPF_OK;
         if (!freeze) {
-            CUDA_TRY(cudaMemcpyAsync(h->exch + (size_t)h->G * K, h->colsum_t_next, sizeof(double) * K,
-                                     cudaMemcpyDeviceToDevice, h->stream));
+            // sharded minibatch: the batch's cells are spread over the ranks; beta needs the sums of all of them
+            if (h->comm && !only_genes) RC_TRY(allreduce_exchange(h, h->stream));
             RC_TRY(beta_update());
         }
     } else {
@@ -950,17 +970,9 @@ int schpf_copy_cell_state(schpf_engine_t *dst, int64_t dst_row0, schpf_engine_t 
     return SCHPF_OK;
 }
 
-// the one exchange step of an iteration, when the engine owns the communicator
-static int allreduce_exchange(schpf_engine_t *h, cudaStream_t stream)
-{
-    return nccl_check(g_nccl.AllReduce(h->exch, h->exch, (size_t)(h->G * h->K + h->K), NCCL_FLOAT64, NCCL_SUM,
-                                       h->comm, stream),
-                      "ncclAllReduce(exchange buffer)");
-}
-
 static int exchange_if_sharded(schpf_engine_t *h, int flags)
 {
-    if (!h->comm || (flags & SCHPF_FREEZE_GENES)) return SCHPF_OK;
+    if (!h->comm || (flags & SCHPF_FREEZE_GENES) || exchange_is_late(flags)) return SCHPF_OK;
     return allreduce_exchange(h, h->stream);
 }
 
@@ -988,7 +1000,7 @@ int schpf_step(schpf_engine_t *h, int n_iters, int flags)
     RC_TRY(check_handle(h));
     RC_TRY(require_ready(h));
     const bool overlap = h->comm && h->xstream && h->opt_overlap_exchange && h->opt_variant == 0 &&
-                         !(flags & SCHPF_FREEZE_GENES);
+                         !(flags & SCHPF_FREEZE_GENES) && !exchange_is_late(flags);
     for (int t = 0; t < n_iters; ++t) {
         if (overlap) {
             RC_TRY(step_overlapped(h, flags));

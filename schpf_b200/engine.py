@@ -11,7 +11,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import CELLS_FIRST, FREEZE_GENES, SIMULTANEOUS, as_f64, as_i32, c_i64, c_int, c_dbl, c_u64, c_vp, dptr
+from ._lib import CELLS_FIRST, FREEZE_GENES, PHASE_CELLS, PHASE_GENES, SIMULTANEOUS, as_f64, as_i32, c_i64, c_int, c_dbl, c_u64, c_vp, dptr
 
 STATE_NAMES = ("theta", "beta", "xi", "eta")
 
@@ -143,13 +143,16 @@ class CaviEngine(object):
         """beta / eta of `other` (same device, ngenes, nfactors) -> this engine, device to device."""
         _lib.check(self._lib.schpf_copy_gene_state(self._h, other._h))
 
-    def step_begin(self, freeze_genes=False, simultaneous=False, random_phi_seed=None):
+    def step_begin(self, freeze_genes=False, simultaneous=False, random_phi_seed=None, cells_first=False):
         mode, seed = (0, 0) if random_phi_seed is None else (1, int(random_phi_seed) & (2 ** 64 - 1))
-        _lib.check(self._lib.schpf_step_begin(self._h, c_int(_flags(freeze_genes, simultaneous)),
+        _lib.check(self._lib.schpf_step_begin(self._h, c_int(_flags(freeze_genes, simultaneous, cells_first)),
                                               c_int(mode), c_u64(seed)))
 
-    def step_end(self, freeze_genes=False, simultaneous=False):
-        _lib.check(self._lib.schpf_step_end(self._h, c_int(_flags(freeze_genes, simultaneous))))
+    def step_end(self, freeze_genes=False, simultaneous=False, cells_first=False, phase=None):
+        """`phase` splits the minibatch order (cells_first) for callers that reduce the exchange buffer
+        themselves: "cells" = theta/xi + the new theta's column sums into the buffer, "genes" = beta/eta."""
+        extra = {None: 0, "cells": PHASE_CELLS, "genes": PHASE_GENES}[phase]
+        _lib.check(self._lib.schpf_step_end(self._h, c_int(_flags(freeze_genes, simultaneous, cells_first) | extra)))
 
     # -- cell sharding with the exchange inside the engine --------------------
     @staticmethod
@@ -350,21 +353,32 @@ class ShardedEngine(object):
             self._buf = self.local.exchange_tensor()
         self._dist.all_reduce(self._buf, op=self._dist.ReduceOp.SUM, group=self.group)
 
-    def step(self, n_iters=1, freeze_genes=False, simultaneous=False, random_phi_seed=None):
+    def step(self, n_iters=1, freeze_genes=False, simultaneous=False, random_phi_seed=None, cells_first=False):
+        """`cells_first` (the minibatch order, scHPF_.py:686-704): theta/xi of this rank's cells of the
+        batch first, THEN the exchange (beta's rate sums the new theta of the whole batch), then beta/eta."""
         n_iters = int(n_iters)
         if self.native:
             if random_phi_seed is not None and n_iters > 0:
-                self.local.step_random_phi(random_phi_seed, freeze_genes, simultaneous)
+                self.local.step_random_phi(random_phi_seed, freeze_genes, simultaneous, cells_first)
                 n_iters -= 1
             if n_iters > 0:
-                self.local.step(n_iters, freeze_genes, simultaneous)
+                self.local.step(n_iters, freeze_genes, simultaneous, cells_first)
             return
+        late = cells_first and not simultaneous and not freeze_genes
         for i in range(n_iters):
-            self.local.step_begin(freeze_genes, simultaneous,
-                                  random_phi_seed if i == 0 else None)
+            self.local.step_begin(freeze_genes, simultaneous, random_phi_seed if i == 0 else None,
+                                  cells_first=cells_first)
+            if late:
+                self.local.step_end(freeze_genes, simultaneous, cells_first=True, phase="cells")
+                self._exchange()
+                self.local.step_end(freeze_genes, simultaneous, cells_first=True, phase="genes")
+                continue
             if not freeze_genes:
                 self._exchange()
-            self.local.step_end(freeze_genes, simultaneous)
+            self.local.step_end(freeze_genes, simultaneous, cells_first=cells_first)
+
+    def close(self):
+        self.local.close()
 
     def loss(self):
         if self.native:

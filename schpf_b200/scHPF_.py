@@ -50,6 +50,14 @@ def _global_row_offset(group, ncells, device=None):
     return int(sum(int(c.item()) for c in counts[:dist.get_rank(group)]))
 
 
+def _total_cells(group, ncells, device=None):
+    import torch
+    import torch.distributed as dist
+    n = torch.tensor([int(ncells)], dtype=torch.int64, device=_dist_device(group, device))
+    dist.all_reduce(n, group=group)
+    return int(n.item())
+
+
 def _mean_over_ranks(group, value, device=None):
     import torch
     import torch.distributed as dist
@@ -397,11 +405,12 @@ class scHPF(BaseEstimator):
                              .format(self.nfactors, MAX_FACTORS))
         nfactors, (ncells, ngenes) = self.nfactors, X.shape
         a, ap, c, cp = self.a, self.ap, self.c, self.cp
-        batched = batchsize is not None and 1 < batchsize <= ncells       # scHPF_.py:627
+        ncells_total = ncells if process_group is None else _total_cells(process_group, ncells, self.device)
+        batched = batchsize is not None and 1 < batchsize <= ncells_total       # scHPF_.py:627 (all ranks' cells)
         multi_device = isinstance(self.device, (list, tuple)) and len(self.device) > 1
-        if batched and (process_group is not None or multi_device):
-            raise NotImplementedError('minibatches (batchsize) and cell sharding (process_group, or a list '
-                                      'of devices) cannot be combined')
+        if batched and multi_device:
+            raise NotImplementedError('minibatches (batchsize) with a list of devices: shard the cells over one '
+                                      'process per GPU (process_group=) instead')
         if process_group is not None and multi_device:
             raise ValueError('give either a process group (one process per GPU) or a list of devices '
                              '(one process for all of them), not both')
@@ -423,8 +432,12 @@ class scHPF(BaseEstimator):
                      xi=(xi.vi_shape, xi.vi_rate), eta=(eta.vi_shape, eta.vi_rate))
         rng = self._rng
         if batched:
+            cell_range = None
+            if process_group is not None:
+                cell_range = (_global_row_offset(process_group, ncells, self.device), ncells_total)
             loop = MinibatchLoop(self._new_engine, X, hyper, state, nfactors, batchsize,
-                                 freeze_genes, beta_theta_simultaneous, rng=rng)
+                                 freeze_genes, beta_theta_simultaneous, rng=rng, process_group=process_group,
+                                 shared_seed=_shared_seed, cell_range=cell_range)
         else:
             engine_options = {}
             if process_group is not None:

@@ -27,7 +27,8 @@ Fixtures
   simul_small.npz   beta_theta_simultaneous=True variant of the loop.
   minibatch_small.npz  scHPF.fit(batchsize=...) (schpf/scHPF_.py:626-631, 642-650, 686-704):
                     A: reinit=True, 240 cells in windows of 64 (wrapping), 9 iterations;
-                    B: reinit=False, windows of 100, beta_theta_simultaneous, loss_smoothing=2.
+                    B: reinit=False, windows of 100, beta_theta_simultaneous, loss_smoothing=2;
+                    C: reinit=False, windows of 100, the default (cells first) order.
   trials_small.npz  run_trials: three seeded restarts (final losses in return order, the best model)
                     and two restarts scored on projected validation cells.
   fp32_small.npz    the same loop with dtype=np.float32 (mixed precision in the reference).
@@ -201,6 +202,15 @@ def minibatch_small():
              beta_theta_simultaneous=True, loss_smoothing=2)
     out.update(B_seed=23, B_batchsize=100, B_iters=8, B_check_freq=2, B_loss=np.array(base.loss))
     out.update(state_dict(base, "B_"))
+    # C: the same seeded init, the default (`batched`) order: theta/xi of the batch first, then beta from the
+    #    same Xphi with the new theta in its rate (scHPF_.py:686-704); the case the sharded minibatch is held to
+    gam = lambda n: schpf.HPF_Gamma(out["B_init_%s_shp" % n].copy(), out["B_init_%s_rte" % n].copy())
+    m3 = scHPF(3, verbose=False, bp=float(out["bp"]), dp=float(out["dp"]), xi=gam("xi"), theta=gam("theta"),
+               eta=gam("eta"), beta=gam("beta"))
+    np.random.seed(24)
+    m3.fit(X, reinit=False, batchsize=100, min_iter=8, max_iter=8, check_freq=2, verbose=False)
+    out.update(C_seed=24, C_batchsize=100, C_iters=8, C_check_freq=2, C_loss=np.array(m3.loss))
+    out.update(state_dict(m3, "C_"))
     np.savez_compressed(os.path.join(HERE, "minibatch_small.npz"), **out)
     print("minibatch_small: loss A", m.loss, "loss B", base.loss)
 

@@ -88,7 +88,7 @@ class OracleEngine(object):
         self.set_state(beta=(o.beta_shp, o.beta_rte), eta=(o.eta_shp, o.eta_rte))
 
     # ---- split phase (cell sharding) ----------------------------------------
-    def step_begin(self, freeze_genes=False, simultaneous=False, random_phi_seed=None, xphi=None):
+    def step_begin(self, freeze_genes=False, simultaneous=False, random_phi_seed=None, xphi=None, cells_first=False):
         s, K = self.st, self.nfactors
         if xphi is not None:
             self._xphi = np.asarray(xphi, dtype=np.float64)
@@ -111,9 +111,31 @@ class OracleEngine(object):
             self._exch = torch.zeros(self.ngenes * self.nfactors + self.nfactors, dtype=torch.float64)
         return self._exch
 
-    def step_end(self, freeze_genes=False, simultaneous=False):
+    def _cells_update(self):
+        s = self.st
+        s.theta_shp = onp.compute_loading_shape_update(self._xphi, self.row, self.ncells, self.a)
+        s.theta_rte = onp.compute_loading_rate_update(s.xi_shp, s.xi_rte, s.beta_shp, s.beta_rte)
+        s.xi_rte = self.bp + (s.theta_shp / s.theta_rte).sum(1)
+
+    def _genes_update(self):
+        s, K = self.st, self.nfactors
+        buf = self.exchange_tensor().numpy()
+        s.beta_shp = self.c + buf[:self.ngenes * K].reshape(self.ngenes, K)
+        s.beta_rte = (s.eta_shp / s.eta_rte)[:, None] + buf[self.ngenes * K:][None, :]
+        s.eta_rte = self.dp + (s.beta_shp / s.beta_rte).sum(1)
+
+    def step_end(self, freeze_genes=False, simultaneous=False, cells_first=False, phase=None):
         s, K = self.st, self.nfactors
         assert not simultaneous
+        if cells_first:
+            # minibatch order (scHPF_.py:686-704): cells first, from the OLD beta; beta's rate sums the NEW theta
+            if phase in (None, "cells"):
+                self._cells_update()
+                if not freeze_genes:
+                    self.exchange_tensor().numpy()[self.ngenes * K:] = (s.theta_shp / s.theta_rte).sum(0)
+            if phase in (None, "genes") and not freeze_genes:
+                self._genes_update()
+            return
         if not freeze_genes:
             buf = self.exchange_tensor().numpy()
             s.beta_shp = self.c + buf[:self.ngenes * K].reshape(self.ngenes, K)

@@ -189,6 +189,23 @@ def test_minibatch_simultaneous_matches_reference(g_minibatch, monkeypatch, devi
 
 
 @pytest.mark.parametrize("device_state", DEVICE_STATE)
+def test_minibatch_default_order_matches_reference(g_minibatch, monkeypatch, device_state):
+    """Case C: seeded init, the default `batched` order."""
+    monkeypatch.setattr(cavi_loop, "MINIBATCH_DEVICE_STATE", device_state)
+    g, X = g_minibatch, _X(g_minibatch)
+    m = scHPF(3, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]),
+              xi=_gam(g, "xi", "B_init_"), theta=_gam(g, "theta", "B_init_"),
+              eta=_gam(g, "eta", "B_init_"), beta=_gam(g, "beta", "B_init_"))
+    np.random.seed(int(g["C_seed"]))
+    m.fit(X, reinit=False, batchsize=int(g["C_batchsize"]), min_iter=int(g["C_iters"]),
+          max_iter=int(g["C_iters"]), check_freq=int(g["C_check_freq"]))
+    for n in NAMES:
+        assert max_rel(getattr(m, n).vi_shape, g["C_%s_shp" % n]) < TOL, n
+        assert max_rel(getattr(m, n).vi_rate, g["C_%s_rte" % n]) < TOL, n
+    assert_allclose(m.loss, g["C_loss"], rtol=1e-11)
+
+
+@pytest.mark.parametrize("device_state", DEVICE_STATE)
 def test_minibatch_larger_problem_against_oracle_loop(monkeypatch, device_state):
     """3000 x 800, K = 20, windows of 700 (gcd 100 -> 30 windows, wraps), 12 iterations from a
     fixed init: the device loop against the same loop driven through the oracle."""

@@ -184,3 +184,63 @@ def test_single_process_two_gpu_fit_matches_unsharded():
     assert abs((m2.beta.vi_shape - m2.c).sum() / X.data.sum() - 1) < 1e-9
     p = m2.project(X, min_iter=2, max_iter=2, check_freq=1)
     assert p.beta == m2.beta and np.isfinite(p.loss[-1])
+
+
+def _minibatch_worker(rank, world, port, out_dir, native):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from scipy.sparse import coo_matrix
+    from schpf_b200 import scHPF, HPF_Gamma
+    from schpf_b200 import engine as eng_mod
+    from schpf_b200.engine import shard_coo_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    if not native:
+        # the split-phase path: theta/xi, torch.distributed all-reduce of the buffer, then beta/eta
+        orig = eng_mod.ShardedEngine.__init__
+        eng_mod.ShardedEngine.__init__ = lambda self, local, group=None, native=None: orig(self, local, group, False)
+    g = dict(np.load(os.path.join(GOLDEN, "minibatch_small.npz")))
+    C, G = (int(v) for v in g["shape"])
+    X, lo, hi = shard_coo_rows(coo_matrix((g["data"], (g["row"], g["col"])), shape=(C, G)), rank, world)
+    gam = lambda n, rows: HPF_Gamma(g["B_init_%s_shp" % n][rows].copy(), g["B_init_%s_rte" % n][rows].copy())
+    m = scHPF(3, verbose=False, device=rank, bp=float(g["bp"]), dp=float(g["dp"]), xi=gam("xi", slice(lo, hi)),
+              theta=gam("theta", slice(lo, hi)), eta=gam("eta", slice(None)), beta=gam("beta", slice(None)))
+    np.random.seed(int(g["C_seed"]) if rank == 0 else 999)
+    m.fit(X, reinit=False, batchsize=int(g["C_batchsize"]), min_iter=int(g["C_iters"]), max_iter=int(g["C_iters"]),
+          check_freq=int(g["C_check_freq"]), process_group=dist.group.WORLD)
+    # reinit=True under sharding: the device's t == 0 draw with one shared seed; must run and stay finite
+    np.random.seed(5)
+    m2 = scHPF(3, verbose=False, device=rank)
+    m2.fit(X, batchsize=120, min_iter=3, max_iter=3, check_freq=1, process_group=dist.group.WORLD)
+    np.savez(os.path.join(out_dir, "mb%d.npz" % rank), lo=lo, hi=hi, loss=np.array(m.loss),
+             theta_shp=m.theta.vi_shape, theta_rte=m.theta.vi_rate, xi_rte=m.xi.vi_rate,
+             beta_shp=m.beta.vi_shape, beta_rte=m.beta.vi_rate, eta_rte=m.eta.vi_rate,
+             loss2=np.array(m2.loss), beta2=m2.beta.vi_shape)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("native", [True, False])
+def test_two_gpu_minibatch_fit_reproduces_the_reference(tmp_path, native):
+    """fit(batchsize=, process_group=) over NCCL: case C of minibatch_small.npz (a seeded minibatch run of
+    the real, single-process reference) with the cells of every window spread over two GPUs; the exchange
+    after the cell update is issued by the engine (native) or by torch.distributed between the two
+    phases of schpf_step_end."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_minibatch_worker, args=(world, _free_port(), str(tmp_path), native), nprocs=world, join=True)
+    g = dict(np.load(os.path.join(GOLDEN, "minibatch_small.npz")))
+    r = [dict(np.load(str(tmp_path / ("mb%d.npz" % k)))) for k in range(world)]
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.abs(b)))
+    for n in ("beta_shp", "beta_rte", "eta_rte", "loss", "beta2", "loss2"):
+        assert np.array_equal(r[0][n], r[1][n]), n
+    for n in ("beta_shp", "beta_rte", "eta_rte"):
+        assert rel(r[0][n], g["C_" + n]) < 1e-9, n
+    for n in ("theta_shp", "theta_rte", "xi_rte"):
+        assert rel(np.concatenate([r[0][n], r[1][n]]), g["C_" + n]) < 1e-9, n
+    assert np.allclose(r[0]["loss"], g["C_loss"], rtol=1e-11)
+    assert np.all(np.isfinite(r[0]["loss2"])) and np.all(np.isfinite(r[0]["beta2"]))

@@ -282,6 +282,24 @@ def test_minibatch_simultaneous_and_smoothing(oracle_backend, g_minibatch, monke
 
 
 @pytest.mark.parametrize("device_state", [False, True])
+def test_minibatch_default_order_from_a_seeded_init(oracle_backend, g_minibatch, monkeypatch, device_state):
+    """Case C: reinit=False, the default `batched` order (cells first, scHPF_.py:686-704)."""
+    from schpf_b200 import cavi_loop
+    monkeypatch.setattr(cavi_loop, "MINIBATCH_DEVICE_STATE", device_state)
+    g, X = g_minibatch, _X(g_minibatch)
+    m = scHPF(3, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]),
+              xi=_gam(g, "xi", "B_init_"), theta=_gam(g, "theta", "B_init_"),
+              eta=_gam(g, "eta", "B_init_"), beta=_gam(g, "beta", "B_init_"))
+    np.random.seed(int(g["C_seed"]))
+    m.fit(X, reinit=False, batchsize=int(g["C_batchsize"]), min_iter=int(g["C_iters"]),
+          max_iter=int(g["C_iters"]), check_freq=int(g["C_check_freq"]))
+    for name in ("theta", "beta", "xi", "eta"):
+        assert max_rel(getattr(m, name).vi_shape, g["C_%s_shp" % name]) < 1e-11
+        assert max_rel(getattr(m, name).vi_rate, g["C_%s_rte" % name]) < 1e-11
+    assert_allclose(m.loss, g["C_loss"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("device_state", [False, True])
 def test_minibatch_edge_cases(oracle_backend, g_minibatch, monkeypatch, device_state):
     from schpf_b200 import cavi_loop
     monkeypatch.setattr(cavi_loop, "MINIBATCH_DEVICE_STATE", device_state)

@@ -198,3 +198,54 @@ def test_custom_loss_and_reinit_under_a_process_group(tmp_path):
     assert len(r[0]["loss"]) < 20                                  # stopped early, together
     assert np.array_equal(r[0]["beta_shp"], r[1]["beta_shp"])      # replicas still identical
     assert int(r[0]["offset"]) == 0 and int(r[1]["offset"]) == int(r[1]["lo"]) > 0
+
+
+def _minibatch_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from scipy.sparse import coo_matrix
+    from schpf_b200 import scHPF, HPF_Gamma
+    from schpf_b200 import scHPF_ as shell
+    from schpf_b200.engine import shard_coo_rows
+    from oracle_engine import OracleEngine
+    shell._engine_factory = OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = dict(np.load(os.path.join(GOLDEN, "minibatch_small.npz")))
+    C, G = (int(v) for v in g["shape"])
+    X, lo, hi = shard_coo_rows(coo_matrix((g["data"], (g["row"], g["col"])), shape=(C, G)), rank, world)
+    gam = lambda n, rows: HPF_Gamma(g["B_init_%s_shp" % n][rows].copy(), g["B_init_%s_rte" % n][rows].copy())
+    cells, genes = slice(lo, hi), slice(None)
+    m = scHPF(3, verbose=False, bp=float(g["bp"]), dp=float(g["dp"]), xi=gam("xi", cells), theta=gam("theta", cells),
+              eta=gam("eta", genes), beta=gam("beta", genes))
+    np.random.seed(int(g["C_seed"]) if rank == 0 else 999)       # the one shuffle comes from rank 0's stream
+    m.fit(X, reinit=False, batchsize=int(g["C_batchsize"]), min_iter=int(g["C_iters"]), max_iter=int(g["C_iters"]),
+          check_freq=int(g["C_check_freq"]), process_group=dist.group.WORLD)
+    np.savez(os.path.join(out_dir, "mb%d.npz" % rank), lo=lo, hi=hi, loss=np.array(m.loss),
+             theta_shp=m.theta.vi_shape, theta_rte=m.theta.vi_rate, xi_rte=m.xi.vi_rate,
+             beta_shp=m.beta.vi_shape, beta_rte=m.beta.vi_rate, eta_rte=m.eta.vi_rate)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_minibatch_fit_with_process_group_reproduces_the_reference(tmp_path):
+    """scHPF.fit(X_shard, batchsize=..., process_group=...): the windows run over ALL cells (rank 0's
+    shuffle), every rank updates the cells of a window it owns, and the one exchange of the iteration
+    follows the cell update.  Two gloo ranks reproduce case C of minibatch_small.npz -- a seeded
+    minibatch run of the REAL, single-process reference (scHPF_.py:626-631, 642-650, 686-704)."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_minibatch_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = dict(np.load(os.path.join(GOLDEN, "minibatch_small.npz")))
+    r = [dict(np.load(str(tmp_path / ("mb%d.npz" % k)))) for k in range(world)]
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.abs(b)))
+    assert int(r[0]["lo"]) == 0 and int(r[0]["hi"]) == int(r[1]["lo"]) and int(r[1]["hi"]) == int(g["shape"][0])
+    for n in ("beta_shp", "beta_rte", "eta_rte", "loss"):
+        assert np.array_equal(r[0][n], r[1][n]), n                       # replicas identical
+    assert rel(r[0]["beta_shp"], g["C_beta_shp"]) < 1e-10 and rel(r[0]["beta_rte"], g["C_beta_rte"]) < 1e-10
+    assert rel(r[0]["eta_rte"], g["C_eta_rte"]) < 1e-10
+    for n in ("theta_shp", "theta_rte", "xi_rte"):
+        assert rel(np.concatenate([r[0][n], r[1][n]]), g["C_" + n]) < 1e-10, n
+    assert np.allclose(r[0]["loss"], g["C_loss"], rtol=1e-10)
