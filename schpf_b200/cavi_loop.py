@@ -25,6 +25,10 @@ MINIBATCH_ENGINE_CACHE = 64
 # Both modes reproduce the reference's seeded minibatch runs (tests/test_gpu_minibatch.py).
 MINIBATCH_DEVICE_STATE = True
 
+# windows that are re-laid out every iteration (more distinct windows than MINIBATCH_ENGINE_CACHE) are cut
+# from a device-resident copy of the permuted matrix by row-pointer slicing (needs torch for the slices)
+DEVICE_WINDOW_SLICES = True
+
 
 class MinibatchSchedule(object):
     """The reference's batch schedule (schpf/util.py:218-231): ONE `np.random.shuffle` of the
@@ -188,6 +192,7 @@ class MinibatchLoop(object):
         self.full = None           # full-matrix engine: loss; in device mode also all cells' theta / xi
         self.full_has_coo = False
         self.Xp_csr = None         # device mode: rows in shuffled order
+        self._dev_rows = None      # ... and their COO arrays on the device (windows that are re-laid out)
 
     @staticmethod
     def _broadcast_order(group, ncells_total, rng):
@@ -224,6 +229,32 @@ class MinibatchLoop(object):
             self.full_has_coo = True
         return self.full
 
+    def _device_rows(self):
+        """The permuted matrix as row-sorted COO arrays ON THE DEVICE plus the host row pointer: a window is
+        then one or two contiguous slices of them (CSR row-pointer slicing) instead of a scipy
+        `tocsr()[ix].tocoo()` and an upload per iteration (the reference's scHPF_.py:645-650)."""
+        if self._dev_rows is None:
+            import torch
+            Xp = self.Xp_csr.tocoo()           # rows ascending, columns ascending within a row
+            dev = torch.device("cuda", int(getattr(self.full, "device", 0)))
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+            self._dev_rows = (up(Xp.row), up(Xp.col), up(Xp.data), np.asarray(self.Xp_csr.indptr, dtype=np.int64))
+        return self._dev_rows
+
+    def _batch_coo_device(self, start):
+        import torch
+        row, col, data, indptr = self._device_rows()
+        rows, cols, vals, at = [], [], [], 0
+        for a, n in self.schedule.pieces(start):
+            lo, hi = int(indptr[a]), int(indptr[a + n])
+            rows.append(row[lo:hi] - (a - at))
+            cols.append(col[lo:hi])
+            vals.append(data[lo:hi])
+            at += n
+        if len(rows) == 1:
+            return rows[0], cols[0], vals[0]
+        return torch.cat(rows), torch.cat(cols), torch.cat(vals)
+
     def _batch_coo(self, start, batch_ix):
         if self.device_state:       # the same rows in the same order, sliced from the permuted matrix
             from scipy.sparse import vstack
@@ -234,7 +265,12 @@ class MinibatchLoop(object):
     def _batch_engine(self, start, batch_ix):
         key = start if self.cache_engines else 0
         eng, Xb = self.engines.get(key), None
-        if eng is None or not self.cache_engines:
+        on_device = (self.device_state and self.process_group is None and not self.cache_engines
+                     and DEVICE_WINDOW_SLICES and hasattr(self.full, "_h"))
+        if on_device and eng is not None:
+            # one engine re-laid out every iteration: the window's triples never leave the device
+            eng.set_coo(*self._batch_coo_device(start))
+        elif eng is None or not self.cache_engines:
             Xb = self._batch_coo(start, batch_ix)
             if eng is not None and eng.ncells != len(batch_ix):     # sharded, not cached: this rank's part varies
                 eng.close()
