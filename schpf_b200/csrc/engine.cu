@@ -655,7 +655,7 @@ int finish_coo(schpf_engine *h)
 
 extern "C" {
 
-int schpf_version(void) { return 200; }
+int schpf_version(void) { return 210; }
 
 const char *schpf_last_error(void) { return g_last_error.c_str(); }
 
