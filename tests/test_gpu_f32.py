@@ -166,3 +166,28 @@ def test_fp32_normaliser_underflow_is_redone_in_log_space():
     oc.cavi_run(data, row, col, st, *hyp, 1, check_freq=0)
     assert max_rel(got["theta"][0], st.theta_shp) < 1e-6
     assert max_rel(got["beta"][0], st.beta_shp) < 1e-6
+
+
+def test_float32_minibatch_and_projection_take_the_fp32_sweep(g20):
+    """every engine a float32 model creates (minibatch windows, the master engine, projections) runs the
+    fp32 sweep; results stay within float32 noise of the float64 model's on the same inputs"""
+    g = g20
+    X = coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(int(v) for v in g["shape"]))
+    out = {}
+    for dt in (np.float32, np.float64):
+        np.random.seed(11)
+        m = scHPF(20, verbose=False, dtype=dt)
+        m.fit(X, batchsize=150, min_iter=12, max_iter=12, check_freq=4)
+        np.random.seed(12)
+        p = m.project(X, min_iter=5, max_iter=5, check_freq=5)
+        assert m.theta.vi_shape.dtype == dt and p.theta.vi_rate.dtype == dt
+        out[dt] = (m, p)
+    (m32, p32), (m64, p64) = out[np.float32], out[np.float64]
+    # the two models start from the same draws rounded to float32 / float64: agreement ~ float32 eps, amplified
+    # by 12 minibatch iterations
+    med = lambda a, b: float(np.median(np.abs(a.astype(np.float64) - b) / np.abs(b)))
+    assert med(m32.beta.vi_shape, m64.beta.vi_shape) < 1e-4
+    assert med(m32.theta.vi_shape, m64.theta.vi_shape) < 1e-4
+    assert_allclose(m32.loss, m64.loss, rtol=1e-3)
+    assert_allclose(p32.loss, p64.loss, rtol=1e-3)
+    assert np.all(np.isfinite(p32.theta.vi_shape)) and np.all(p32.theta.vi_shape > 0)
