@@ -325,7 +325,8 @@ __device__ __forceinline__ void slow_enqueue(const SweepArgs &A, int own, int ot
     const unsigned long long at = atomicAdd(A.slow_count, 1ULL);
     if (at < A.slow_cap) A.slow_queue[at] = make_int4(own, oth_global, __double2hiint(y), __double2loint(y));
 }
-int launch_slow_fixup(cudaStream_t s, const SweepArgs &args, int *overflow_flag);
+// redo the queued nonzeros of one sweep direction, or of both (B != nullptr) with one launch
+int launch_slow_fixup(cudaStream_t s, const SweepArgs &A, const SweepArgs *B, int *overflow_flag);
 
 int launch_sweep(int mode, int K, const SideLayout &L, const SweepArgs &args, cudaStream_t stream);
 // one-lane-per-owner kernels (sweep_lanes.cu)

@@ -185,12 +185,22 @@ __global__ void literal_kernel(int64_t nnz, int K, const int32_t *__restrict__ r
 // reference does every nonzero (hpf_numba.py:98-112: log space, max subtracted) and added to the
 // owner's `direct` row.  Launched after every shape sweep with a small fixed grid; the queue is
 // empty unless priors are far below 1e-2, and the kernel then costs one read.
-__global__ void slow_fixup_kernel(const int4 *__restrict__ queue, const unsigned long long *__restrict__ count,
-                                  unsigned int cap, int K, const double *__restrict__ own_elog,
-                                  const double *__restrict__ oth_elog, double *__restrict__ direct,
+struct FixupSide {
+    const int4 *queue;
+    const unsigned long long *count;
+    const double *own_elog, *oth_elog;
+    double *direct;
+};
+
+// blockIdx.y selects the sweep direction (one launch redoes both queues)
+__global__ void slow_fixup_kernel(FixupSide s0, FixupSide s1, unsigned int cap, int K,
                                   unsigned long long *__restrict__ slow_hits, int *__restrict__ overflow)
 {
-    unsigned long long n = *count;
+    const FixupSide S = blockIdx.y == 0 ? s0 : s1;
+    const int4 *__restrict__ queue = S.queue;
+    const double *__restrict__ own_elog = S.own_elog, *__restrict__ oth_elog = S.oth_elog;
+    double *__restrict__ direct = S.direct;
+    unsigned long long n = *S.count;
     if (n == 0) return;
     if (n > cap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 1);
@@ -412,10 +422,11 @@ __global__ void capacity_rate_kernel(int64_t n, int K, const double *__restrict_
         }                                                                                   \
     } while (0)
 
-int launch_slow_fixup(cudaStream_t s, const SweepArgs &A, int *overflow_flag)
+int launch_slow_fixup(cudaStream_t s, const SweepArgs &A, const SweepArgs *B, int *overflow_flag)
 {
-    slow_fixup_kernel<<<64, 128, 0, s>>>(A.slow_queue, A.slow_count, A.slow_cap, A.K, A.own_elog, A.oth_elog,
-                                         A.direct, A.slow_hits, overflow_flag);
+    const FixupSide a{A.slow_queue, A.slow_count, A.own_elog, A.oth_elog, A.direct};
+    const FixupSide b = B ? FixupSide{B->slow_queue, B->slow_count, B->own_elog, B->oth_elog, B->direct} : a;
+    slow_fixup_kernel<<<dim3(64, B ? 2 : 1), 128, 0, s>>>(a, b, A.slow_cap, A.K, A.slow_hits, overflow_flag);
     LAUNCH_CHECK();
     return SCHPF_OK;
 }

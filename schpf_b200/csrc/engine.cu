@@ -348,7 +348,7 @@ int zero_accumulators(schpf_engine *h, bool genes_too)
     return SCHPF_OK;
 }
 
-int cells_sweep(schpf_engine *h)
+int cells_sweep(schpf_engine *h, SweepArgs *defer_fixup = nullptr)
 {
     // theta side: cells own, gene panels stream through shared memory
     SweepArgs A = side_args(h, h->cells);
@@ -359,11 +359,15 @@ int cells_sweep(schpf_engine *h)
     A.oth_elog = h->elog_b;
     A.direct = h->direct_t;
     RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->cells, A));
+    if (defer_fixup) {           // the caller redoes both directions' queues with one launch
+        *defer_fixup = A;
+        return SCHPF_OK;
+    }
     h->n_launches += 1;
-    return launch_slow_fixup(h->stream, A, h->overflow);
+    return launch_slow_fixup(h->stream, A, nullptr, h->overflow);
 }
 
-int genes_sweep(schpf_engine *h)
+int genes_sweep(schpf_engine *h, SweepArgs *defer_fixup = nullptr)
 {
     // beta side: genes own, cell panels stream
     SweepArgs B = side_args(h, h->genes);
@@ -374,24 +378,30 @@ int genes_sweep(schpf_engine *h)
     B.oth_elog = h->elog_t;
     B.direct = h->direct_b;
     RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->genes, B));
+    if (defer_fixup) {
+        *defer_fixup = B;
+        return SCHPF_OK;
+    }
     h->n_launches += 1;
-    return launch_slow_fixup(h->stream, B, h->overflow);
+    return launch_slow_fixup(h->stream, B, nullptr, h->overflow);
 }
 
 // this shard's beta shape sums + column sums of theta.e_x (theta BEFORE its update,
 // scHPF_.py:701-703) into the exchange buffer
-int fold_exchange_buffer(schpf_engine *h)
+int fold_exchange_buffer(schpf_engine *h, bool fold = true)
 {
     const int K = h->K;
-    RC_TRY(launch_fold(h->stream, h->G, K, h->geom_b(), h->Eb, h->acc_b, h->direct_b, h->exch));
+    // fold == false (one GPU, schpf_step): the beta finalisation reads the accumulators itself, only the
+    // K column sums of theta.e_x are parked in the buffer's tail (theta's finalisation overwrites its own copy)
+    if (fold) RC_TRY(launch_fold(h->stream, h->G, K, h->geom_b(), h->Eb, h->acc_b, h->direct_b, h->exch));
     CUDA_TRY(cudaMemcpyAsync(h->exch + (size_t)h->G * K, h->colsum_t_next, sizeof(double) * K,
                              cudaMemcpyDeviceToDevice, h->stream));
-    h->n_launches += 1;
+    if (fold) h->n_launches += 1;
     return SCHPF_OK;
 }
 
 // mode 0: E-step from the resident state; 1: random phi; 2: Xphi supplied (already scattered by caller)
-int step_begin_impl(schpf_engine *h, int flags, int mode, uint64_t seed)
+int step_begin_impl(schpf_engine *h, int flags, int mode, uint64_t seed, bool fold = true)
 {
     const bool freeze = flags & SCHPF_FREEZE_GENES;
     const int K = h->K;
@@ -407,11 +417,15 @@ int step_begin_impl(schpf_engine *h, int flags, int mode, uint64_t seed)
                                   nullptr, h->direct_t, freeze ? nullptr : h->direct_b));
             h->n_launches += 1;
         } else {
-            RC_TRY(cells_sweep(h));
-            if (!freeze) RC_TRY(genes_sweep(h));
+            // both directions' underflow queues are redone by ONE launch (empty queues cost one read each)
+            SweepArgs A, B;
+            RC_TRY(cells_sweep(h, &A));
+            if (!freeze) RC_TRY(genes_sweep(h, &B));
+            RC_TRY(launch_slow_fixup(h->stream, A, freeze ? nullptr : &B, h->overflow));
+            h->n_launches += 1;
         }
     }
-    if (!freeze) RC_TRY(fold_exchange_buffer(h));
+    if (!freeze) RC_TRY(fold_exchange_buffer(h, fold));
     return SCHPF_OK;
 }
 
@@ -426,7 +440,7 @@ int allreduce_exchange(schpf_engine *h, cudaStream_t stream)
 // the minibatch order exchanges AFTER the cell update (inside step_end_impl), not between the phases
 inline bool exchange_is_late(int flags) { return (flags & SCHPF_CELLS_FIRST) && !(flags & SCHPF_SIMULTANEOUS); }
 
-int step_end_impl(schpf_engine *h, int flags)
+int step_end_impl(schpf_engine *h, int flags, bool folded = true)
 {
     const bool freeze = flags & SCHPF_FREEZE_GENES;
     const bool simultaneous = flags & SCHPF_SIMULTANEOUS;
@@ -452,7 +466,10 @@ int step_end_impl(schpf_engine *h, int flags)
     auto beta_update = [&]() -> int {
         // scHPF_.py:699-704
         CUDA_TRY(cudaMemsetAsync(h->colsum_b, 0, sizeof(double) * K, h->stream));
-        RC_TRY(launch_finalize(h->stream, h->G, K, h->geom_b(), h->c, h->dp, h->exch, h->Eb, nullptr, nullptr,
+        // folded: the (all-reduced) exchange buffer holds the genes' sums; otherwise they are still Eb * acc_b +
+        // direct_b -- the same fma the fold kernel would have done, so the result is bit-identical
+        RC_TRY(launch_finalize(h->stream, h->G, K, h->geom_b(), h->c, h->dp, folded ? h->exch : nullptr, h->Eb,
+                               folded ? nullptr : h->acc_b, folded ? nullptr : h->direct_b,
                                h->exch + (size_t)h->G * K, h->eta_shp, h->eta_rte, h->beta_shp, h->beta_rte,
                                h->elog_b, h->Eb, h->colsum_b));
         h->n_launches += 1;
@@ -1006,9 +1023,10 @@ int schpf_step(schpf_engine_t *h, int n_iters, int flags)
             RC_TRY(step_overlapped(h, flags));
             continue;
         }
-        RC_TRY(step_begin_impl(h, flags, 0, 0));
+        const bool fold = h->comm != nullptr;      // one GPU: no exchange, beta is finalised from the accumulators
+        RC_TRY(step_begin_impl(h, flags, 0, 0, fold));
         RC_TRY(exchange_if_sharded(h, flags));
-        RC_TRY(step_end_impl(h, flags));
+        RC_TRY(step_end_impl(h, flags, fold));
     }
     return SCHPF_OK;
 }
