@@ -3,8 +3,8 @@
 
     python tools/sass_summary.py [lib.so] > profiles/r2_sass_summary.json
 
-For every `sweep_kernel<KP,MODE,PACKED>` (lane pairs) and `lane_sweep_kernel<NA,REM,MODE,YHI>`
-(one lane per owner) instantiation: registers, spill bytes and shared memory from
+For every `sweep_kernel<KP,MODE,PACKED>` (lane pairs), `lane_sweep_kernel<NA,REM,MODE,ENC>` (one lane per
+owner) and `lane_sweep_f32_kernel<NP,MODE,PACKED>` (fp32) instantiation: registers, spill bytes and shared memory from
 `cuobjdump --dump-resource-usage`, instruction counts of the whole kernel, and the same counts
 restricted to the HOT LOOP (the innermost backward branch whose body holds LDS.128 row loads) --
 which is what answers "are the STL/LDL inside the loop".  Mnemonics of interest: UBLKCP (1-D bulk
@@ -19,15 +19,19 @@ import sys
 from collections import Counter
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-WATCH = ("UBLKCP", "UBLKRED", "SYNCS", "DMMA", "LDS", "DFMA", "DMUL", "DADD", "DSETP", "MUFU", "I2F", "STL", "LDL", "REDG",
+WATCH = ("UBLKCP", "UBLKRED", "SYNCS", "DMMA", "LDS", "DFMA", "DMUL", "DADD", "DSETP", "FFMA", "FMUL", "FADD", "MUFU", "I2F", "I2FP", "STL", "LDL", "REDG",
          "ATOMG", "LDG", "BAR", "LOP3", "IMAD", "ISETP")
 
 
 def demangle_name(sym):
-    m = re.search(r"lane_sweep_kernelILi(\d+)ELi(\d+)ELi(\d+)ELb(\d)", sym)
+    m = re.search(r"lane_sweep_f32_kernelILi(\d+)ELi(\d+)ELb(\d)", sym)
     if m:
-        na, rem, mode, yhi = (int(x) for x in m.groups())
-        return "lane_sweep_kernel<KP=%d,%s,%s>" % (16 * na + 4 * rem, "LLH" if mode else "SHAPE", "yhi" if yhi else "int")
+        planes, mode, packed = (int(x) for x in m.groups())
+        return "lane_sweep_f32_kernel<floats=%d,%s,%s>" % (32 * planes, "LLH" if mode else "SHAPE", "packed" if packed else "wide")
+    m = re.search(r"lane_sweep_kernelILi(\d+)ELi(\d+)ELi(\d+)ELi(\d)", sym)
+    if m:
+        na, rem, mode, enc = (int(x) for x in m.groups())
+        return "lane_sweep_kernel<KP=%d,%s,%s>" % (16 * na + 4 * rem, "LLH" if mode else "SHAPE", ("wide-int", "wide-yhi", "packed")[enc])
     m = re.search(r"sweep_kernelILi(\d+)ELi(\d+)ELb(\d)", sym)
     if m:
         kp, mode, packed = (int(x) for x in m.groups())
