@@ -160,13 +160,14 @@ parse_lines_kernel(const char *__restrict__ text, int64_t begin, int64_t end, in
     }
 }
 
+// device temporaries of one schpf_parse_triples call
 struct IngestPlan {
     int nblocks = 0;
-    int *counts = nullptr;
-    int64_t *first = nullptr;
-    void *tmp = nullptr;
+    int *counts = nullptr;              // data lines per block
+    int64_t *first = nullptr;           // their exclusive prefix sum = first output index of a block
+    void *tmp = nullptr;                // CUB work area
     size_t tmp_bytes = 0;
-    unsigned long long *err = nullptr;
+    unsigned long long *err = nullptr;  // byte offset of the first malformed line (all ones = none)
 };
 
 }  // namespace
@@ -199,10 +200,11 @@ int schpf_count_lines(int device, void *stream_v, const char *d_text, int64_t nb
     CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&counts), sizeof(int) * (size_t)nblocks, stream));
     CUDA_TRY(pool_malloc(reinterpret_cast<void **>(&total), sizeof(int64_t), stream));
     count_lines_kernel<<<nblocks, INGEST_THREADS, 0, stream>>>(d_text, begin, nbytes, counts);
+    cudaError_t e = cudaGetLastError();
     size_t tmp_bytes = 0;
     cub::DeviceReduce::Sum(nullptr, tmp_bytes, counts, total, nblocks, stream);
     void *tmp = nullptr;
-    cudaError_t e = pool_malloc(&tmp, tmp_bytes ? tmp_bytes : 1, stream);
+    if (e == cudaSuccess) e = pool_malloc(&tmp, tmp_bytes ? tmp_bytes : 1, stream);
     if (e == cudaSuccess) e = cub::DeviceReduce::Sum(tmp, tmp_bytes, counts, total, nblocks, stream);
     int64_t h = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h, total, sizeof(int64_t), cudaMemcpyDeviceToHost, stream);
@@ -257,6 +259,7 @@ int schpf_parse_triples(int device, void *stream_v, const char *d_text, int64_t 
     if (e == cudaSuccess) {
         e = cudaMemsetAsync(P.err, 0xff, sizeof(unsigned long long), stream);
         count_lines_kernel<<<P.nblocks, INGEST_THREADS, 0, stream>>>(d_text, begin, nbytes, P.counts);
+        if (e == cudaSuccess) e = cudaGetLastError();
         if (e == cudaSuccess)
             e = cub::DeviceScan::ExclusiveSum(P.tmp, P.tmp_bytes, P.counts, P.first, P.nblocks, stream);
         parse_lines_kernel<<<P.nblocks, INGEST_THREADS, 0, stream>>>(d_text, begin, nbytes, nfields, index_base, P.first,
