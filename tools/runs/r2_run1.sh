@@ -5,7 +5,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r2_run1.sh'
 T=${1:-r2a}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${T}_smi.txt 2>&1
 SCHPF_TEST_UNVALIDATED=1 timeout 700 python -m pytest tests -m gpu -q > gpurun_out/${T}_tests_gpu.log 2>&1
 echo "gpu suite rc=$?"; tail -5 gpurun_out/${T}_tests_gpu.log

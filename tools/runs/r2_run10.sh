@@ -2,7 +2,7 @@
 # Round 2: ingest tests + timing, K=30 with two steps per block, whole suite.
 T=${1:-r2j}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 600 python -m pytest tests/test_gpu_ingest.py -m gpu -q > gpurun_out/${T}_tests_ingest.log 2>&1
 echo "ingest tests rc=$?"; tail -30 gpurun_out/${T}_tests_ingest.log
 timeout 600 python tools/time_ingest.py 20000 20000 1000 > gpurun_out/${T}_ingest.json 2> gpurun_out/${T}_ingest.err

@@ -1,7 +1,7 @@
 #!/bin/bash
 T=${1:-r2l}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 600 python tools/time_ingest.py 20000 20000 1000 > gpurun_out/${T}_ingest.json 2> gpurun_out/${T}_ingest.err
 echo "ingest timing rc=$?"; cat gpurun_out/${T}_ingest.json; tail -3 gpurun_out/${T}_ingest.err
 SCHPF_TRACE=1 SCHPF_BENCH_VERBOSE=1 timeout 300 python bench.py --no-cpu --no-strong --no-parity > gpurun_out/${T}_trace.json 2> gpurun_out/${T}_trace.err

@@ -2,7 +2,7 @@
 # Round 2: packed 4-byte entries for the one-lane streams: tests, then packed vs wide at K = 16 / 20 / 30 and fp32.
 T=${1:-r2m}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_tests.log 2>&1
 echo "tests rc=$?"; tail -8 gpurun_out/${T}_tests.log
 run() {   # tag K extra...

@@ -1,7 +1,7 @@
 #!/bin/bash
 T=${1:-r2n}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 600 python -m pytest tests/test_gpu_lanes.py tests/test_gpu_engine.py -m gpu -q -x > gpurun_out/${T}_tests.log 2>&1
 echo "tests rc=$?"; tail -3 gpurun_out/${T}_tests.log
 run() {   # tag K extra...

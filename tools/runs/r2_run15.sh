@@ -1,7 +1,7 @@
 #!/bin/bash
 T=${1:-r2p}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_tests.log 2>&1
 echo "tests rc=$?"; tail -3 gpurun_out/${T}_tests.log
 run() {   # tag lib K extra...

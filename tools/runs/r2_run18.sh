@@ -3,7 +3,7 @@
 # finalize kernel, launch list of the default step, cfg-2 line.
 T=${1:-r2s}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 cap() {   # name regex extra bench flags...
   local name=$1 rx=$2; shift 2
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$rx -s 9 -c 2 -f \

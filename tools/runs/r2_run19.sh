@@ -2,7 +2,7 @@
 # Round 2, final check of the tree as committed: whole GPU suite, smoke, the default bench line, the fp32 line.
 T=${1:-r2t}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${T}_tests.log 2>&1
 echo "tests rc=$?"; tail -3 gpurun_out/${T}_tests.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${T}_smoke.log 2>&1

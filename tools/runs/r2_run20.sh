@@ -2,7 +2,7 @@
 # Round 2: the default bench line at N ranks (library version 210).
 T=${1:-r2u}; N=${2:-8}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
 SCHPF_BENCH_VERBOSE=1 timeout 600 $TR bench.py --gpus $N > gpurun_out/${T}_bench_n$N.json 2> gpurun_out/${T}_bench_n$N.err
 echo "bench N=$N rc=$?"; grep "bench r0" gpurun_out/${T}_bench_n$N.err | tail -4

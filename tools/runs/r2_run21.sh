@@ -2,7 +2,7 @@
 # mid-size problem (20k x 20k, 2e7 nnz): where does a step go when the sweeps are short?
 T=${1:-r2w}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 200 python bench.py --no-cpu --no-strong --no-parity --cells 20000 --draws 1000 --steps 100 --warmup 5 > gpurun_out/${T}_mid.json 2> gpurun_out/${T}_mid.err
 python -c "
 import json

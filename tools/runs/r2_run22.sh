@@ -1,7 +1,7 @@
 #!/bin/bash
 T=${1:-r2x}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_tests.log 2>&1
 echo "tests rc=$?"; tail -3 gpurun_out/${T}_tests.log
 timeout 200 python bench.py --no-cpu --no-strong --no-parity --no-e2e --cells 20000 --draws 1000 --steps 100 --warmup 5 > gpurun_out/${T}_mid.json 2> gpurun_out/${T}_mid.err

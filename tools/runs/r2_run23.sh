@@ -2,7 +2,7 @@
 # chunked panel fills: tests, then 1 / 4 / 8 / 16 chunks at K = 16 / 20 / 30 (cfg-3) and K = 20 on the mid-size matrix
 T=${1:-r2z}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 900 python -m pytest tests/test_gpu_lanes.py tests/test_gpu_engine.py tests/test_gpu_kernels.py -m gpu -q -x > gpurun_out/${T}_tests.log 2>&1
 echo "tests rc=$?"; tail -3 gpurun_out/${T}_tests.log
 run() {   # tag lib K extra...

@@ -3,7 +3,7 @@
 # alone, both), the schedule-free K=20 stream, 16 warps, and ncu captures of the lane kernels.
 T=${1:-r2c}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 600 python -m pytest tests/test_gpu_lanes.py tests/test_gpu_engine.py -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1
 echo "tests rc=$?"; tail -5 gpurun_out/${T}_tests.log
 run() {   # tag lib K extra...

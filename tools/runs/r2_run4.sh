@@ -1,22 +1,23 @@
 #!/bin/bash
-# Round 2: whole GPU suite (fp32 tests included), then build variants of the lane sweep at K = 16 / 20 / 30.
-T=${1:-r2i}
+# Round 2, fourth GPU call: whole GPU suite, prefetch variants of the lane sweep, then the full default bench line.
+T=${1:-r2d}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${T}_tests.log 2>&1
-echo "tests rc=$?"; tail -12 gpurun_out/${T}_tests.log
+cd "$(dirname "$0")/../.."
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1
+echo "tests rc=$?"; tail -6 gpurun_out/${T}_tests.log
 run() {   # tag lib K extra...
   local tag=$1 lib=$2 K=$3; shift 3
   SCHPF_B200_LIB=$lib timeout 120 python bench.py --no-cpu --no-e2e --no-strong --no-parity --factors $K --steps 20 --warmup 3 "$@" \
       > gpurun_out/${T}_${tag}_K$K.json 2> gpurun_out/${T}_${tag}_K$K.err
 }
 D=$PWD/schpf_b200/_C/libschpf_b200.so
-for K in 16 20 30; do run base $D $K; done
-for tag in ctas2 pf0 l2a16 ns32_2; do
+for K in 15 16 17 20 30 32; do run lanes $D $K; done
+run sched $D 20 --free-schedule 0
+for tag in pf0 w16_12 w16_12pf0 l2a16 l2a4; do
   L=$PWD/schpf_b200/_C_$tag/libschpf_b200.so
   [ -f $L ] || continue
   case $tag in
-    ns32_2) Ks="30" ;;
+    w16_12|w16_12pf0) Ks="16" ;;
     *) Ks="16 20 30" ;;
   esac
   for K in $Ks; do run $tag $L $K; done
@@ -34,3 +35,5 @@ for f in sorted(glob.glob("gpurun_out/%s_*_K*.json" % sys.argv[1])):
     except Exception as e:
         print(f, "unreadable", e, open(f[:-5] + ".err").read()[-300:])
 P
+SCHPF_BENCH_VERBOSE=1 timeout 600 python bench.py > gpurun_out/${T}_bench_full.json 2> gpurun_out/${T}_bench_full.err
+echo "full bench rc=$?"; cut -c1-600 gpurun_out/${T}_bench_full.json; tail -5 gpurun_out/${T}_bench_full.err

@@ -3,7 +3,7 @@
 # across K, ncu captures of the lane kernels the bench times, launch list, full default bench line.
 T=${1:-r2e}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1
 echo "tests rc=$?"; tail -6 gpurun_out/${T}_tests.log
 run() {   # tag K extra...

@@ -2,7 +2,7 @@
 # Round 2, N-GPU call: the NCCL parity tests (need >= 2 GPUs) and the default bench line at N ranks.
 T=${1:-r2f}; N=${2:-2}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 600 python -m pytest tests/test_gpu_sharded.py tests/test_gpu_minibatch.py -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1
 echo "tests rc=$?"; tail -4 gpurun_out/${T}_tests.log
 SCHPF_BENCH_VERBOSE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \

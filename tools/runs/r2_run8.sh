@@ -2,7 +2,7 @@
 # Round 2: fp32 sweep -- tests, bench lines (separate from the headline), ncu capture; launch list of the fp64 step.
 T=${1:-r2h}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 600 python -m pytest tests/test_gpu_f32.py -m gpu -q > gpurun_out/${T}_tests_f32.log 2>&1
 echo "f32 tests rc=$?"; tail -25 gpurun_out/${T}_tests_f32.log
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1
