@@ -559,6 +559,8 @@ def main():
         opts["precision"] = 32
     if args.packed >= 0:
         opts["packed_entries"] = args.packed
+    if os.environ.get("SCHPF_NO_OVERLAP_SWEEPS"):
+        opts["overlap_sweeps"] = 0          # A/B switch: the two shape sweeps one after the other on one stream
     if args.rank_per_range >= 0:
         opts["rank_per_range"] = args.rank_per_range
     if args.free_schedule >= 0:

@@ -123,7 +123,8 @@ int schpf_destroy(schpf_engine_t *h);
  * entry stream and resident layout; -1 default = where it is not slower (one-lane K <= 16 and the fp32
  * sweep), 0 = never, 1 = wherever the stream allows it), "overlap_exchange" (default 1: with an attached
  * communicator schpf_step runs the all-reduce on a second stream underneath the cells-own sweep;
- * 0 = in order on the engine's stream), "lanes" (default 1: K <= 20 and 29..32 run the
+ * 0 = in order on the engine's stream), "overlap_sweeps" (default 1: the two shape sweeps of an iteration start
+ * together, the cells-own one on a second stream, so that one grid's last partial wave is filled by the other's CTAs), "lanes" (default 1: K <= 20 and 29..32 run the
  * one-lane-per-owner sweep; 0 = lane-pair sweep for every K), "rank_per_range" (-1 automatic),
  * "precision" (64 default; 32 = the fp32 sweep used for dtype=np.float32 models, scHPF_.py:225-246:
  * table entries, dot product, quotient and per-panel sums in fp32, everything else fp64) */

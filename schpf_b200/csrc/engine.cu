@@ -187,6 +187,11 @@ struct schpf_engine {
     int opt_overlap_exchange = 1;
     cudaStream_t xstream = nullptr;
     cudaEvent_t ev_folded = nullptr, ev_reduced = nullptr;
+    // the two shape sweeps of an iteration are independent: the cells-own one runs on a second stream, so the
+    // tail of one grid (a last partial wave of CTAs) is filled by the other's CTAs (option "overlap_sweeps")
+    int opt_overlap_sweeps = 1;
+    cudaStream_t sstream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // counters
     double n_iterations = 0, n_sweeps = 0, n_shape_sweeps = 0, n_launches = 0;
@@ -241,6 +246,45 @@ void free_coo(schpf_engine *h)
     h->cells.release();
     h->genes.release();
     h->have_coo = false;
+}
+
+int launch_one_sweep(schpf_engine *h, int mode, const SideLayout &L, const SweepArgs &args, cudaStream_t stream)
+{
+    if (h->f32) RC_TRY(launch_f32_sweep(mode, h->K, L, args, stream));
+    else if (L.opw == 32) RC_TRY(launch_lane_sweep(mode, h->K, L, args, stream));
+    else RC_TRY(launch_sweep(mode, h->K, L, args, stream));
+    h->n_sweeps += 1;
+    if (mode == SWEEP_SHAPE) h->n_shape_sweeps += 1;
+    h->n_launches += 1;
+    return SCHPF_OK;
+}
+
+// event pair of the timing option, recorded on the engine's stream around what the caller launches
+int timing_begin(schpf_engine *h, int mode, cudaEvent_t *e1_out)
+{
+    *e1_out = nullptr;
+    if (!h->opt_timing) return SCHPF_OK;
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreate(&a));
+        CUDA_TRY(cudaEventCreate(&b));
+        h->ev_pool.emplace_back(a, b);
+        h->ev_mode.push_back(0);
+    }
+    h->ev_mode[h->ev_used] = mode;
+    CUDA_TRY(cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream));
+    *e1_out = h->ev_pool[h->ev_used].second;
+    ++h->ev_used;
+    return SCHPF_OK;
+}
+
+int ensure_sweep_stream(schpf_engine *h)
+{
+    if (h->sstream) return SCHPF_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->sstream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    return SCHPF_OK;
 }
 
 int timed_sweep(schpf_engine *h, int mode, const SideLayout &L, const SweepArgs &args)
@@ -348,7 +392,7 @@ int zero_accumulators(schpf_engine *h, bool genes_too)
     return SCHPF_OK;
 }
 
-int cells_sweep(schpf_engine *h, SweepArgs *defer_fixup = nullptr)
+int cells_sweep(schpf_engine *h, SweepArgs *defer_fixup = nullptr, cudaStream_t untimed_on = nullptr)
 {
     // theta side: cells own, gene panels stream through shared memory
     SweepArgs A = side_args(h, h->cells);
@@ -358,7 +402,9 @@ int cells_sweep(schpf_engine *h, SweepArgs *defer_fixup = nullptr)
     A.own_elog = h->elog_t;
     A.oth_elog = h->elog_b;
     A.direct = h->direct_t;
-    RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->cells, A));
+    // untimed_on: launched on that stream with no events of its own (the caller times the concurrent pair)
+    if (untimed_on) RC_TRY(launch_one_sweep(h, SWEEP_SHAPE, h->cells, A, untimed_on));
+    else RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->cells, A));
     if (defer_fixup) {           // the caller redoes both directions' queues with one launch
         *defer_fixup = A;
         return SCHPF_OK;
@@ -367,7 +413,7 @@ int cells_sweep(schpf_engine *h, SweepArgs *defer_fixup = nullptr)
     return launch_slow_fixup(h->stream, A, nullptr, h->overflow);
 }
 
-int genes_sweep(schpf_engine *h, SweepArgs *defer_fixup = nullptr)
+int genes_sweep(schpf_engine *h, SweepArgs *defer_fixup = nullptr, bool untimed = false)
 {
     // beta side: genes own, cell panels stream
     SweepArgs B = side_args(h, h->genes);
@@ -377,7 +423,8 @@ int genes_sweep(schpf_engine *h, SweepArgs *defer_fixup = nullptr)
     B.own_elog = h->elog_b;
     B.oth_elog = h->elog_t;
     B.direct = h->direct_b;
-    RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->genes, B));
+    if (untimed) RC_TRY(launch_one_sweep(h, SWEEP_SHAPE, h->genes, B, h->stream));
+    else RC_TRY(timed_sweep(h, SWEEP_SHAPE, h->genes, B));
     if (defer_fixup) {
         *defer_fixup = B;
         return SCHPF_OK;
@@ -419,8 +466,22 @@ int step_begin_impl(schpf_engine *h, int flags, int mode, uint64_t seed, bool fo
         } else {
             // both directions' underflow queues are redone by ONE launch (empty queues cost one read each)
             SweepArgs A, B;
-            RC_TRY(cells_sweep(h, &A));
-            if (!freeze) RC_TRY(genes_sweep(h, &B));
+            if (!freeze && h->opt_overlap_sweeps) {
+                // cells-own sweep on the second stream, genes-own on the engine's: one train of CTAs, one tail
+                RC_TRY(ensure_sweep_stream(h));
+                cudaEvent_t e1 = nullptr;
+                RC_TRY(timing_begin(h, SWEEP_SHAPE, &e1));
+                CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));
+                CUDA_TRY(cudaStreamWaitEvent(h->sstream, h->ev_fork, 0));
+                RC_TRY(cells_sweep(h, &A, h->sstream));
+                RC_TRY(genes_sweep(h, &B, true));
+                CUDA_TRY(cudaEventRecord(h->ev_join, h->sstream));
+                CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+                if (e1) CUDA_TRY(cudaEventRecord(e1, h->stream));
+            } else {
+                RC_TRY(cells_sweep(h, &A));
+                if (!freeze) RC_TRY(genes_sweep(h, &B));
+            }
             RC_TRY(launch_slow_fixup(h->stream, A, freeze ? nullptr : &B, h->overflow));
             h->n_launches += 1;
         }
@@ -764,6 +825,13 @@ int schpf_destroy(schpf_engine_t *h)
         cudaEventDestroy(h->ev_reduced);
         h->xstream = nullptr;
     }
+    if (h->sstream) {
+        cudaStreamSynchronize(h->sstream);
+        cudaStreamDestroy(h->sstream);
+        cudaEventDestroy(h->ev_fork);
+        cudaEventDestroy(h->ev_join);
+        h->sstream = nullptr;
+    }
     free_coo(h);
     dev_free(h->theta_shp); dev_free(h->theta_rte); dev_free(h->beta_shp); dev_free(h->beta_rte);
     dev_free(h->xi_shp); dev_free(h->xi_rte); dev_free(h->eta_shp); dev_free(h->eta_rte);
@@ -795,6 +863,7 @@ int schpf_set_option(schpf_engine_t *h, const char *key, int64_t value)
     else if (!strcmp(key, "packed_entries")) h->opt_packed_entries = (int)value;
     else if (!strcmp(key, "row_offset")) h->row_offset = value;
     else if (!strcmp(key, "overlap_exchange")) h->opt_overlap_exchange = (int)value;
+    else if (!strcmp(key, "overlap_sweeps")) h->opt_overlap_sweeps = (int)value;
     else if (!strcmp(key, "lanes")) h->opt_lanes = (int)value;
     else if (!strcmp(key, "precision")) {
         if (value != 32 && value != 64) {
@@ -1001,6 +1070,30 @@ static int step_overlapped(schpf_engine_t *h, int flags)
 {
     RC_TRY(ensure_tables(h));
     RC_TRY(zero_accumulators(h, true));
+    if (h->opt_overlap_sweeps) {
+        // both sweeps start together (cells-own on its own stream); the fold and the all-reduce follow the
+        // genes-own sweep alone and hide under what is left of the cells-own one
+        RC_TRY(ensure_sweep_stream(h));
+        SweepArgs A;
+        cudaEvent_t e1 = nullptr;
+        RC_TRY(timing_begin(h, SWEEP_SHAPE, &e1));
+        CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->sstream, h->ev_fork, 0));
+        RC_TRY(cells_sweep(h, &A, h->sstream));
+        CUDA_TRY(cudaEventRecord(h->ev_join, h->sstream));
+        RC_TRY(genes_sweep(h, nullptr, true));
+        RC_TRY(fold_exchange_buffer(h));
+        CUDA_TRY(cudaEventRecord(h->ev_folded, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->xstream, h->ev_folded, 0));
+        RC_TRY(allreduce_exchange(h, h->xstream));
+        CUDA_TRY(cudaEventRecord(h->ev_reduced, h->xstream));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        if (e1) CUDA_TRY(cudaEventRecord(e1, h->stream));
+        RC_TRY(launch_slow_fixup(h->stream, A, nullptr, h->overflow));
+        h->n_launches += 1;
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_reduced, 0));
+        return step_end_impl(h, flags);
+    }
     RC_TRY(genes_sweep(h));
     RC_TRY(fold_exchange_buffer(h));
     CUDA_TRY(cudaEventRecord(h->ev_folded, h->stream));
