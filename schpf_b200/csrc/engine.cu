@@ -1079,9 +1079,11 @@ static int step_overlapped(schpf_engine_t *h, int flags)
         RC_TRY(timing_begin(h, SWEEP_SHAPE, &e1));
         CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));
         CUDA_TRY(cudaStreamWaitEvent(h->sstream, h->ev_fork, 0));
+        // genes-own FIRST: CTAs are dispatched in launch order, so it also finishes first and its fold and
+        // all-reduce run while the cells-own sweep still has CTAs to go
+        RC_TRY(genes_sweep(h, nullptr, true));
         RC_TRY(cells_sweep(h, &A, h->sstream));
         CUDA_TRY(cudaEventRecord(h->ev_join, h->sstream));
-        RC_TRY(genes_sweep(h, nullptr, true));
         RC_TRY(fold_exchange_buffer(h));
         CUDA_TRY(cudaEventRecord(h->ev_folded, h->stream));
         CUDA_TRY(cudaStreamWaitEvent(h->xstream, h->ev_folded, 0));
