@@ -102,17 +102,17 @@ def _parse(text, begin, nfields, index_base, capacity, device):
     return row[:n], col[:n], val[:n]
 
 
-def load_mtx(path, device=0):
-    """MatrixMarket coordinate file -> DeviceCOO (cells x genes as stored; the reference's `prep`
-    writes cells as rows)."""
-    text, raw = _upload(path, device)
-    # header: banner, comments, size line -- a few lines at the top, read on the host
-    head = bytes(raw[:1 << 22])
+def parse_mtx_header(head, total_bytes=None, path="<mtx>"):
+    """The few lines in front of the data of a MatrixMarket file: banner, comments, size line.
+    `head` = the first bytes of the file.  Returns (nrows, ncols, nnz, field, offset of the first data
+    byte).  Raises ValueError for anything that is not a `matrix coordinate` file with field integer /
+    real / pattern and symmetry `general` (what the reference's `prep` writes, bin/scHPF:327,361)."""
+    total_bytes = len(head) if total_bytes is None else total_bytes
     pos, banner, size = 0, None, None
     while size is None:
         nl = head.find(b"\n", pos)
         if nl < 0:
-            if len(head) < raw.size or pos >= len(head):
+            if len(head) < total_bytes or pos >= len(head):
                 raise ValueError("%s: no size line in the first %d bytes" % (path, len(head)))
             nl = len(head)                                   # last line without a newline
         line = head[pos:nl].decode("ascii", "replace").strip()
@@ -132,8 +132,21 @@ def load_mtx(path, device=0):
                          "(integer | real | pattern, general)" % (path, field, symmetry))
     if len(size) != 3:
         raise ValueError("%s: bad size line %r" % (path, " ".join(size)))
-    nrows, ncols, nnz = (int(v) for v in size)
-    row, col, val = _parse(text, min(pos, raw.size), 2 if field == "pattern" else 3, 1, nnz, device)
+    try:
+        nrows, ncols, nnz = (int(v) for v in size)
+    except ValueError:
+        raise ValueError("%s: bad size line %r" % (path, " ".join(size)))
+    if nrows < 0 or ncols < 0 or nnz < 0:
+        raise ValueError("%s: bad size line %r" % (path, " ".join(size)))
+    return nrows, ncols, nnz, field, min(pos, total_bytes)
+
+
+def load_mtx(path, device=0):
+    """MatrixMarket coordinate file -> DeviceCOO (cells x genes as stored; the reference's `prep`
+    writes cells as rows)."""
+    text, raw = _upload(path, device)
+    nrows, ncols, nnz, field, begin = parse_mtx_header(bytes(raw[:1 << 22]), raw.size, path)
+    row, col, val = _parse(text, begin, 2 if field == "pattern" else 3, 1, nnz, device)
     if int(row.numel()) != nnz:
         raise ValueError("%s: size line announces %d entries, file holds %d" % (path, nnz, int(row.numel())))
     if nnz and (int(row.max()) >= nrows or int(col.max()) >= ncols):

@@ -516,3 +516,30 @@ def test_fit_on_a_list_of_devices_shards_the_cells_in_one_process(oracle_backend
     assert abs((m2.beta.vi_shape - m2.c).sum() / X.data.sum() - 1) < 1e-9
     with pytest.raises(NotImplementedError):
         scHPF(5, verbose=False, device=[0, 1]).fit(X, batchsize=100, max_iter=1, min_iter=1)
+
+
+# ------------------------------------------------------------------ ingest ---
+def test_mtx_header_parsing_matches_scipy(tmp_path):
+    """host half of schpf_b200.io.load_mtx (the data lines are parsed on the device): size line and data
+    offset agree with what scipy.io.mminfo / mmread see for files written by the reference's writer"""
+    from scipy.io import mminfo, mmwrite
+    from schpf_b200.io import parse_mtx_header
+    X = coo_matrix((np.array([3, 1, 2], dtype=np.int32), (np.array([0, 2, 2]), np.array([1, 0, 3]))), shape=(3, 5))
+    for field, comment in (("integer", ""), ("real", "two\nlines"), ("pattern", "x")):
+        path = str(tmp_path / ("h_%s.mtx" % field))
+        mmwrite(path, X.astype(np.float64) if field == "real" else X, field=field, comment=comment)
+        raw = open(path, "rb").read()
+        nrows, ncols, nnz, fld, begin = parse_mtx_header(raw)
+        assert (nrows, ncols, nnz, fld) == (mminfo(path)[0], mminfo(path)[1], mminfo(path)[2], field)
+        data = [l for l in raw[begin:].decode().splitlines() if l.strip()]
+        assert len(data) == nnz and data[0].split()[:2] == ["1", "2"]
+    ok = b"%%MatrixMarket matrix coordinate integer general\n% c\n\n2 2 1\n1 1 5"
+    assert parse_mtx_header(ok) == (2, 2, 1, "integer", ok.index(b"1 1 5"))
+    for bad, msg in ((b"1 1 1\n", "banner"), (b"%%MatrixMarket matrix array real general\n1 1\n", "coordinate"),
+                     (b"%%MatrixMarket matrix coordinate complex general\n1 1 1\n", "field"),
+                     (b"%%MatrixMarket matrix coordinate integer symmetric\n1 1 1\n", "symmetry"),
+                     (b"%%MatrixMarket matrix coordinate integer general\n% only comments\n", "size line"),
+                     (b"%%MatrixMarket matrix coordinate integer general\n1 1\n", "size line"),
+                     (b"%%MatrixMarket matrix coordinate integer general\n1 x 1\n", "size line")):
+        with pytest.raises(ValueError, match=msg):
+            parse_mtx_header(bad)
