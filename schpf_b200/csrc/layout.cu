@@ -258,9 +258,24 @@ __global__ void place_entries_kernel(int64_t n_qw, int npanel, int opw, bool fre
             const int64_t src0 = first4[base0 + o * ostride];      // the owner's four class lists are contiguous
             const int pos = stream_pos(q0 + o, opw);
             const int cnt_o = n[o][0] + n[o][1] + n[o][2] + n[o][3];
+            // Rotated class lists (K 17..20: list c of the owner in slot s holds the rows of bank class c + s):
+            // taken ROUND-ROBIN, list (step mod 4) at every step while it lasts, the four owners of a
+            // scheduling group read four different bank classes at the same step -- in phase at every step
+            // instead of only while four class-major runs happen to have the same length.  Streams without
+            // classes have everything in list 0 and come out in the sorted order as before.
+            int l0 = 0, l1 = n[o][0], l2 = l1 + n[o][1], l3 = l2 + n[o][2];      // cursors of the four lists
+            const int h0 = l1, h1 = l2, h2 = l3, h3 = cnt_o;                       // (registers: no indexed arrays)
             for (int step = 0; step < cnt_o; ++step) {
                 const int64_t dst = ((pair0 + (step >> 1)) * opw + pos) * 2 + (step & 1);
-                const uint64_t v = vals[src0 + step];
+                const unsigned avail = (l0 < h0 ? 1u : 0u) | (l1 < h1 ? 2u : 0u) | (l2 < h2 ? 4u : 0u) | (l3 < h3 ? 8u : 0u);
+                const int want = step & 3;
+                const int c = (want + __ffs(((avail | (avail << 4)) >> want) & 0xfu) - 1) & 3;   // first list with entries from `want` on
+                const int at = c == 0 ? l0 : c == 1 ? l1 : c == 2 ? l2 : l3;
+                l0 += c == 0;
+                l1 += c == 1;
+                l2 += c == 2;
+                l3 += c == 3;
+                const uint64_t v = vals[src0 + at];
                 if (PACKED)
                     reinterpret_cast<uint32_t *>(entries_v)[dst] = pack_entry((uint32_t)v, (uint32_t)(v >> 32), false);
                 else
