@@ -223,9 +223,14 @@ def _minibatch_worker(rank, world, port, out_dir):
     np.random.seed(int(g["C_seed"]) if rank == 0 else 999)       # the one shuffle comes from rank 0's stream
     m.fit(X, reinit=False, batchsize=int(g["C_batchsize"]), min_iter=int(g["C_iters"]), max_iter=int(g["C_iters"]),
           check_freq=int(g["C_check_freq"]), process_group=dist.group.WORLD)
+    # reinit=True: random initialisation, and the batch's t == 0 random-phi step with one seed for all ranks
+    np.random.seed(50 + rank)
+    m2 = scHPF(3, verbose=False)
+    m2.fit(X, batchsize=120, min_iter=4, max_iter=4, check_freq=1, process_group=dist.group.WORLD)
     np.savez(os.path.join(out_dir, "mb%d.npz" % rank), lo=lo, hi=hi, loss=np.array(m.loss),
              theta_shp=m.theta.vi_shape, theta_rte=m.theta.vi_rate, xi_rte=m.xi.vi_rate,
-             beta_shp=m.beta.vi_shape, beta_rte=m.beta.vi_rate, eta_rte=m.eta.vi_rate)
+             beta_shp=m.beta.vi_shape, beta_rte=m.beta.vi_rate, eta_rte=m.eta.vi_rate,
+             loss2=np.array(m2.loss), beta2=m2.beta.vi_shape, theta2=m2.theta.vi_shape)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -249,3 +254,7 @@ def test_minibatch_fit_with_process_group_reproduces_the_reference(tmp_path):
     for n in ("theta_shp", "theta_rte", "xi_rte"):
         assert rel(np.concatenate([r[0][n], r[1][n]]), g["C_" + n]) < 1e-10, n
     assert np.allclose(r[0]["loss"], g["C_loss"], rtol=1e-10)
+    # the reinit=True fit: same gene side and loss on both ranks, everything finite and positive
+    assert np.array_equal(r[0]["beta2"], r[1]["beta2"]) and np.array_equal(r[0]["loss2"], r[1]["loss2"])
+    assert len(r[0]["loss2"]) == 4 and np.all(np.isfinite(r[0]["loss2"]))
+    assert all(np.all(r[k]["theta2"] > 0) for k in range(world)) and np.all(r[0]["beta2"] > 0)
